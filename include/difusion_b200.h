@@ -1,0 +1,193 @@
+/*
+ * difusion_b200 -- C-ABI of the B200-native DI-Fusion per-frame map hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one operator of the reference's
+ * torch-extension layer (system/ext/__init__.py:13-42 and third-party torch_scatter) or one fused
+ * stretch of system/map.py / system/tracker.py.  The reference interface each one replaces is cited.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  All pointers are DEVICE pointers unless the name
+ *     starts with h_ (host).  Arrays are dense row-major.  `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success, a negative DFB_E_* code otherwise; dfb_last_error() gives the message
+ *     (thread-local).  No exceptions cross the ABI.  Kernel launch errors ARE checked (the reference
+ *     never checks them, imgproc/common.cuh:7-9).
+ *   - no hidden allocation: temporaries live in a caller-provided workspace (`ws`, `ws_bytes`), sized by the
+ *     companion *_ws_bytes() function.  Calls are asynchronous on `stream`; data-dependent output sizes
+ *     are written to device counters the caller reads.
+ *   - built for sm_100a only; there is no CPU fallback.
+ */
+#ifndef DIFUSION_B200_H_
+#define DIFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_OK 0
+#define DFB_E_INVALID (-1)   /* bad argument */
+#define DFB_E_WORKSPACE (-2) /* workspace too small */
+#define DFB_E_CUDA (-3)      /* CUDA runtime / launch error */
+#define DFB_E_CAPACITY (-4)  /* a fixed-capacity structure overflowed */
+
+#define DFB_LATENT_DIM 29
+#define DFB_DIV_IEEE 0  /* x / vs   : torch CPU semantics (the parity oracle, BASELINE config 1) */
+#define DFB_DIV_RECIP 1 /* x * (1/vs): torch CUDA semantics for division by a Python scalar    */
+
+int dfb_version(void);
+const char* dfb_last_error(void);
+/* SM count / name of the current device (so hosts can size grids); returns 0 or DFB_E_CUDA. */
+int dfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network weights.  Host code folds weight-norm / batch-norm and packs the blobs
+ * (nerf-fusion_b200/weights.py documents the layout); sizes are validated here.
+ * Replaces: network/utility.py:22-58 load_model + the per-forward weight-norm recompute
+ * (network/utility.py:211-220) and BatchNorm eval (utils/pt_util.py:193-206).
+ * ---------------------------------------------------------------------------------------------- */
+size_t dfb_decoder_blob_floats(void);
+size_t dfb_encoder_blob_floats(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 -- image / point-cloud preprocessing
+ * ---------------------------------------------------------------------------------------------- */
+/* system.ext.unproject_depth (imgproc.cpp:3, imgproc.cu:5-44).  depth (H,W) f32, NaN = invalid ->
+ * pc (H,W,3) f32.  Invalid pixels get NaN in ALL three channels (the reference leaves 1,2 uninitialised). */
+int dfb_unproject_depth(const float* depth, int H, int W, float fx, float fy, float cx, float cy, float* pc,
+                        void* stream);
+
+/* system.ext.remove_radius_outlier (pcproc.cpp:3-7, pcproc.cu:160-187): mask[i] = (the nb_points-th smallest
+ * squared distance from point i, self included) < radius^2.  pc (n,4) f32 with w = 0. */
+size_t dfb_pcproc_ws_bytes(int n);
+int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radius, uint8_t* mask, void* ws,
+                              size_t ws_bytes, void* stream);
+/* system.ext.estimate_normals (pcproc.cpp:9-14, pcproc.cu:189-210): PCA normal over the <= max_nn-1 nearest
+ * neighbours within radius (>= 5 required, else NaN), oriented towards cam.  max_nn <= 32. */
+int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, const float* h_cam_xyz,
+                         float* normals, void* ws, size_t ws_bytes, void* stream);
+
+/* torch_scatter.scatter_mean(src, index, dim=0) (tracker.py:22-23).  src (n,d) f32, index (n,) i64 in
+ * [0, n_out).  out (n_out,d) f32; empty groups give 0.  Deterministic: rows are summed in ascending row
+ * order.  */
+size_t dfb_scatter_mean_ws_bytes(int n, int n_out);
+int dfb_scatter_mean(const float* src, const int64_t* index, int n, int d, int n_out, float* out, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* tracker.point_box_filter (tracker.py:14-24) fused: bounding box, cell keys, unique (ascending key),
+ * per-cell mean of points and normals.  out_points/out_normals hold up to n rows; *d_n_out (device int32)
+ * receives the number of cells.  div_mode selects how (p - min)/voxel_size is evaluated (DFB_DIV_*). */
+size_t dfb_box_filter_ws_bytes(int n);
+int dfb_point_box_filter(const float* points, const float* normals, int n, float voxel_size, int div_mode,
+                         float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* system.ext.groupby_sum (indexing.cpp:3-4, indexing.cu:59-71,89-109): sum (C,L) f32 and count (C,) i32 of
+ * values (n,L) grouped by indices (n,) i64.  Outputs are zeroed here. */
+int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, int C, float* sum, int32_t* count,
+                    void* stream);
+
+/* system.ext.gradient_xy (imgproc.cpp:21, photometric.cu:3-22,79-93). (H,W) -> (H,W,2), NaN border. */
+int dfb_gradient_xy(const float* intensity, int H, int W, float* grad, void* stream);
+/* system.ext.rgb_odometry (imgproc.cpp:14-20, photometric.cu:24-77,95-138).  f (H,W) and, if J != NULL,
+ * J (H,W,6); NaN where invalid.  h_intr = fx,fy,cx,cy; h_krkinv row-major 3x3; h_kt 3. */
+int dfb_rgb_odometry(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D,
+                     const float* cur_dIdxy, int H, int W, const float* h_intr, const float* h_krkinv,
+                     const float* h_kt, float min_grad_scale, float max_depth_delta, float* f, float* J,
+                     void* stream);
+/* Fused tracker.compute_rgb_Hg (tracker.py:136-177): the same per-pixel residual/Jacobian reduced in-kernel to
+ * out[0..35] = sum w J J^T (with the reference's sign flip J := -J), out[36..41] = sum w f J, out[42] = sum w f^2,
+ * out[43] = number of valid pixels (doubles, unnormalised).  `out44` must hold 80 doubles: [0..43] is the result,
+ * the rest is scratch; all of it is zeroed here.  robust: 0 none, 1 huber, 2 tukey. */
+int dfb_rgb_hg(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D,
+               const float* cur_dIdxy, int H, int W, const float* h_intr, const float* h_krkinv, const float* h_kt,
+               float min_grad_scale, float max_depth_delta, int robust, float robust_k, int compute_J, double* out44,
+               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stages 2+3 -- integrate_keyframe (system/map.py:341-453, do_optimize = False)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t nx, ny, nz;          /* grid size (map.py:178)                                   */
+  float bound_min[3];          /* map.py:182                                               */
+  float voxel_size;            /* map.py:177                                               */
+  int32_t div_mode;            /* DFB_DIV_*                                                */
+  int32_t prune_min_vox_obs;   /* fusion-lr-kt.yaml:32, strict '>'  (map.py:376)           */
+  float ignore_count_th;       /* :33, strict '>' (map.py:572,632)                         */
+  float encoder_count_th;      /* :34, strict '<' (map.py:410)                             */
+} dfb_map_params;
+
+/* Persistent per-map scratch (all-zero between calls; the kernels restore the zeros they disturb):
+ *   grid_count  int32[G]            per-cell point counter
+ *   grid_bits   uint32[ceil(G/32)]  allocation bitmap
+ *   acc         float[cap*29], acc_n int32[cap], touched int32[cap]   per-slot encoder accumulators        */
+size_t dfb_integrate_ws_bytes(int n, int64_t n_cells);
+
+/* Phase A (map.py:367-388 up to the allocation count): voxel ids, count-prune (unq_mask, the function's return
+ * value map.py:520), mark unseen home voxels and their 6 clamped face neighbours, count them.
+ * *d_n_new (device int32) receives how many slots phase B will allocate, so the host can grow its buffers
+ * exactly like map.py:263-285 before calling phase B. */
+int dfb_integrate_plan(const dfb_map_params* h_params, const float* xyz, const float* normal, int n,
+                       const int64_t* indexer, int32_t* grid_count, uint32_t* grid_bits, uint8_t* unq_mask,
+                       int32_t* d_n_new, void* ws, size_t ws_bytes, void* stream);
+/* Phase B (map.py:388-453): assign slots n_occupied.. in ascending voxel-id order, gather (point, offset)
+ * samples of candidate voxels, run the encoder MLP, scatter-add per voxel, running-mean update, mark
+ * updated slots.  `ws` must be the workspace phase A filled, unq_mask phase A's mask, n_new the value read from
+ * *d_n_new.  capacity = rows of the per-slot arrays (DFB_E_CAPACITY if n_occupied + n_new exceeds it).
+ * d_stats (device int32[4]) receives {n_samples, n_voxels_updated, n_allocated, 0}. */
+int dfb_integrate_commit(const dfb_map_params* h_params, const float* normal, const uint8_t* unq_mask, int n,
+                         int64_t* indexer, float* latent_vecs, int64_t* latent_vecs_pos, float* voxel_obs_count,
+                         uint8_t* updated_flag, int64_t n_occupied, int64_t capacity, int32_t n_new, uint32_t* grid_bits,
+                         float* acc, int32_t* acc_n, int32_t* touched, const float* encoder_blob, int32_t* d_stats,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* network encoder forward on explicit inputs (map.py:446-447 -> di_encoder.py:26-30): x (m,6) -> (m,29). */
+int dfb_encoder_forward(const float* x, int m, const float* encoder_blob, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 4 -- decoder queries
+ * ---------------------------------------------------------------------------------------------- */
+/* net_util.forward_model on explicit rows (utility.py:61 -> di_decoder.py:55-86): x (n,32) = [latent, xyz]
+ * -> sdf (n,), std (n,). */
+int dfb_decoder_forward(const float* x, int n, const float* decoder_blob, float* sdf, float* std, void* stream);
+
+/* DenseIndexedMap.get_sdf (map.py:560-580), un-compacted: for every xyz row writes valid[i] (u8) and, where
+ * valid, sdf[i], std[i].  If g_sdf/g_std/grad_xyz are non-NULL it also back-propagates
+ * grad_xyz[i] = d(g_sdf[i]*sdf_i + g_std[i]*std_i)/d xyz_i  (what autograd does on the reference graph). */
+int dfb_get_sdf(const dfb_map_params* h_params, const float* xyz, int n, const int64_t* indexer,
+                const float* latent_vecs, const float* voxel_obs_count, const float* decoder_blob, float* sdf,
+                float* std, uint8_t* valid, const float* g_sdf, const float* g_std, float* grad_xyz, void* stream);
+
+/* SDFTracker.compute_sdf_Hg (tracker.py:179-223) fused: transform, map lookup, decoder forward + reverse pass,
+ * Jacobian, robust weights, reduction.  obs_xyz (n,3) camera space.  h_pose = 33 floats:
+ * R_total(9), t_total(3), R_delta(9), t_delta(3), R_last(9) (row-major, fp32 casts of the f64 poses).
+ * out44 (device doubles, 80 allocated: 44 results + scratch, zeroed here): [0..35] sum w J J^T, [36..41] sum w r J, [42] sum w r^2, [43] M' (valid
+ * count) -- unnormalised; the host divides by M' like tracker.py:215-223.  robust: 0 none, 1 huber, 2 tukey. */
+int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, const float* h_pose,
+               const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
+               const float* decoder_blob, int robust, float robust_k, int compute_J, double* out44, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 5 -- meshing
+ * ---------------------------------------------------------------------------------------------- */
+/* do_meshing sampling (map.py:637-688, fast=True): per voxel slot occ[b], decode an r^3 lattice, trilinear
+ * x2 (align_corners), re-decode the |sdf| < refine_band samples, negate.  cube_sdf/std (B,2r,2r,2r). */
+size_t dfb_decode_cubes_ws_bytes(int B, int r);
+int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r, float refine_band,
+                     const float* decoder_blob, float* cube_sdf, float* cube_std, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* system.ext.marching_cubes_interp (mc.cpp:3-12, mc_interp_kernel.cu:202-382).  indexer (nx,ny,nz) i64,
+ * valid_blocks (U,) i64, vec_batch_mapping (n_map,) i32, cubes (B,2r,2r,2r).  Writes up to max_tri triangles
+ * (tri (T,3,3) f32 voxel units, flat_id (T,) i64, tri_std (T,3) f32) and the TOTAL count found to *d_n_tri
+ * (device int32; may exceed max_tri, in which case the output is truncated like mc_interp_kernel.cu:375-379). */
+int dfb_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int64_t* valid_blocks, int U,
+                       const int32_t* vec_batch_mapping, int n_map, const float* cube_sdf, const float* cube_std,
+                       int B, int r, float max_std, int max_tri, float* tri, int64_t* flat_id, float* tri_std,
+                       int32_t* d_n_tri, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFUSION_B200_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libdifusion_b200.so (the C-ABI in include/difusion_b200.h).
+
+The library is built in-tree by ``csrc/Makefile`` (``__graft_entry__.build()``).  There is no CPU fallback: if the
+shared object is missing or a call fails, this module raises.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libdifusion_b200.so"
+
+
+class DfbError(RuntimeError):
+    pass
+
+
+class MapParams(C.Structure):
+    """dfb_map_params (include/difusion_b200.h)."""
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("div_mode", C.c_int32),
+                ("prune_min_vox_obs", C.c_int32), ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_SZ = C.c_size_t
+_I64 = C.c_int64
+_FP = C.POINTER(C.c_float)
+_MP = C.POINTER(MapParams)
+
+# name -> (restype, argtypes); every symbol include/difusion_b200.h declares
+SIGNATURES = {
+    "dfb_version": (_I, []),
+    "dfb_last_error": (C.c_char_p, []),
+    "dfb_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "dfb_decoder_blob_floats": (_SZ, []),
+    "dfb_encoder_blob_floats": (_SZ, []),
+    "dfb_unproject_depth": (_I, [_P, _I, _I, _F, _F, _F, _F, _P, _P]),
+    "dfb_pcproc_ws_bytes": (_SZ, [_I]),
+    "dfb_remove_radius_outlier": (_I, [_P, _I, _I, _F, _P, _P, _SZ, _P]),
+    "dfb_estimate_normals": (_I, [_P, _I, _I, _F, _FP, _P, _P, _SZ, _P]),
+    "dfb_scatter_mean_ws_bytes": (_SZ, [_I, _I]),
+    "dfb_scatter_mean": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "dfb_box_filter_ws_bytes": (_SZ, [_I]),
+    "dfb_point_box_filter": (_I, [_P, _P, _I, _F, _I, _P, _P, _P, _P, _SZ, _P]),
+    "dfb_groupby_sum": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "dfb_gradient_xy": (_I, [_P, _I, _I, _P, _P]),
+    "dfb_rgb_odometry": (_I, [_P, _P, _P, _P, _P, _I, _I, _FP, _FP, _FP, _F, _F, _P, _P, _P]),
+    "dfb_rgb_hg": (_I, [_P, _P, _P, _P, _P, _I, _I, _FP, _FP, _FP, _F, _F, _I, _F, _I, _P, _P]),
+    "dfb_integrate_ws_bytes": (_SZ, [_I, _I64]),
+    "dfb_integrate_plan": (_I, [_MP, _P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dfb_integrate_commit": (_I, [_MP, _P, _P, _I, _P, _P, _P, _P, _P, _I64, _I64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dfb_encoder_forward": (_I, [_P, _I, _P, _P, _P]),
+    "dfb_decoder_forward": (_I, [_P, _I, _P, _P, _P, _P]),
+    "dfb_get_sdf": (_I, [_MP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dfb_sdf_hg": (_I, [_MP, _P, _I, _FP, _P, _P, _P, _P, _I, _F, _I, _P, _P]),
+    "dfb_decode_cubes_ws_bytes": (_SZ, [_I, _I]),
+    "dfb_decode_cubes": (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
+    "dfb_marching_cubes": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and type every entry point.  Raises DfbError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("DFB_LIB", LIB_PATH))
+    if not path.exists():
+        raise DfbError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(nvcc, sm_100a).  difusion_b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DfbError(f"difusion_b200 call failed ({rc}): {load().dfb_last_error().decode()}")
+
+
+def fptr(values):
+    """host float array argument"""
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr

@@ -1,0 +1,168 @@
+// Error plumbing, device info and the shared scan primitive.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256;
+constexpr int SCAN_E = 8;
+constexpr int SCAN_TILE = SCAN_T * SCAN_E;
+
+template <bool POPC>
+__device__ __forceinline__ int scan_load(const void* in, int i, int n) {
+  if (i >= n) return 0;
+  if (POPC) return __popc(((const uint32_t*)in)[i]);
+  return ((const int*)in)[i];
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int warp_tot[SCAN_T / 32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = lane < SCAN_T / 32 ? warp_tot[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    if (lane < SCAN_T / 32) warp_tot[lane] = ti - t;  // exclusive warp offsets
+    if (lane == SCAN_T / 32 - 1) *total = ti;
+  }
+  __syncthreads();
+  int r = warp_tot[w] + inc - v;
+  return r;
+}
+
+template <bool POPC>
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const void* in, int n, int* block_sums) {
+  __shared__ int tot;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
+  int s = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_E; ++e) s += scan_load<POPC>(in, base + e, n);
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_of_sums(int* block_sums, int nb, int* total) {
+  __shared__ int tot;
+  int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
+    int i = b0 + threadIdx.x;
+    int v = i < nb ? block_sums[i] : 0;
+    int ex = block_excl_scan(v, &tot);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    block_sums[nb] = carry;
+    if (total) *total = carry;
+  }
+}
+
+template <bool POPC>
+__global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, int n, const int* block_sums) {
+  __shared__ int tot;
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
+  int v[SCAN_E];
+  int s = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_E; ++e) {
+    v[e] = scan_load<POPC>(in, base + e, n);
+    s += v[e];
+  }
+  int ex = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int e = 0; e < SCAN_E; ++e) {
+    if (base + e < n) out[base + e] = ex;
+    ex += v[e];
+  }
+}
+
+template <bool POPC>
+static int scan_impl(const void* in, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
+  if (n <= 0) {
+    if (total) DFB_CUDA(cudaMemsetAsync(total, 0, sizeof(int), s));
+    return DFB_OK;
+  }
+  int nb = div_up(n, SCAN_TILE);
+  scan_tile_sums<POPC><<<nb, SCAN_T, 0, s>>>(in, n, block_sums);
+  scan_of_sums<<<1, SCAN_T, 0, s>>>(block_sums, nb, total);
+  scan_apply<POPC><<<nb, SCAN_T, 0, s>>>(in, out, n, block_sums);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
+  return scan_impl<false>(in, out, n, block_sums, total, s);
+}
+int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
+  return scan_impl<true>(words, out, n, block_sums, total, s);
+}
+
+// expands the packed 29 doubles (21 upper-tri, 6, 1, 1) into the public 44-double layout
+__global__ void hg_expand_kernel(const double* packed, double* out44) {
+  int t = threadIdx.x;
+  if (t < 36) {
+    int a = t / 6, b = t % 6;
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+    out44[t] = packed[idx];
+  } else if (t < 42) out44[t] = packed[21 + (t - 36)];
+  else if (t == 42) out44[42] = packed[27];
+  else if (t == 43) out44[43] = packed[28];
+}
+
+
+void launch_hg_expand(const double* packed, double* out44, cudaStream_t s) { hg_expand_kernel<<<1, 64, 0, s>>>(packed, out44); }
+
+}  // namespace dfb
+
+extern "C" {
+int dfb_version(void) { return 100; }
+const char* dfb_last_error(void) { return dfb::g_err; }
+int dfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  DFB_CUDA(cudaGetDevice(&dev));
+  if (sm_count) DFB_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) DFB_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) DFB_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return DFB_OK;
+}
+}

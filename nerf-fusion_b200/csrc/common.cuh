@@ -1,0 +1,161 @@
+// Shared helpers for the difusion_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/difusion_b200.h"
+
+namespace dfb {
+
+void set_error(const char* fmt, ...);
+
+#define DFB_CHECK_ARG(cond, msg)                  \
+  do {                                            \
+    if (!(cond)) {                                \
+      dfb::set_error("invalid argument: %s", msg); \
+      return DFB_E_INVALID;                       \
+    }                                             \
+  } while (0)
+
+#define DFB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      dfb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFB_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define DFB_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      dfb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFB_E_CUDA;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    T* r = (T*)(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+int sm_count();
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Warp-aggregated append: every lane with `pred` gets a unique slot from *counter with ONE atomic per warp.
+__device__ __forceinline__ int warp_append(int* counter, bool pred) {
+  unsigned m = __ballot_sync(0xffffffffu, pred);
+  int lane = threadIdx.x & 31;
+  int base = 0;
+  if (m) {
+    int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+  }
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// order-preserving float <-> uint map for atomicMin/Max on floats
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// x / vs with the selected torch semantics, never contracted.
+__device__ __forceinline__ float div_vs(float x, float vs, float inv_vs, int div_mode) {
+  return div_mode == DFB_DIV_IEEE ? __fdiv_rn(x, vs) : __fmul_rn(x, inv_vs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of int32 (3 kernels, any n).  block_sums: ceil(n/2048)+1 ints of scratch.
+// total (sum of all) is written to *total if non-null.
+// ------------------------------------------------------------------------------------------------
+int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s);
+// same but the input is popcount(words[i])
+int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// Gauss-Newton reduction helpers shared by the SDF and photometric terms
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float robust_w(float x, int kind, float k) {
+  if (kind == 1) { float a = fabsf(x); return a > k ? k / a : 1.0f; }                       // tracker.py:61-66
+  if (kind == 2) { float t = x / k; float s = 1.f - t * t; return fabsf(x) <= k ? s * s : 0.f; }  // :67-71
+  return 1.0f;
+}
+
+// Block-level reduction of NV doubles per thread into out[] with one atomic per value per block.
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce_atomic(const float* vals, double* out) {
+  __shared__ double red[THREADS / 32][NV];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double d = warp_sum((double)vals[k]);
+    if (lane == 0) red[w][k] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < THREADS / 32; ++ww) s += red[ww][threadIdx.x];
+    if (s != 0.0) atomicAdd(&out[threadIdx.x], s);
+  }
+}
+
+// Accumulate sum w J J^T (upper triangle, 21), sum w r J (6), sum w r^2, count into acc[29].
+__device__ __forceinline__ void hg_accumulate(float* acc, const float* J, float r, float w, bool with_J) {
+  if (with_J) {
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[t++] += w * J[a] * J[b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += w * r * J[a];
+  }
+  acc[27] += w * r * r;
+  acc[28] += 1.0f;
+}
+
+
+// expands the packed 29 doubles (21 upper-tri, 6, 1, 1) into the public 44-double layout
+void launch_hg_expand(const double* packed, double* out44, cudaStream_t s);
+
+}  // namespace dfb

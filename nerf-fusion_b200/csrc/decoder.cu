@@ -1,0 +1,403 @@
+// Stage 4 (decoder queries) and the sampling half of stage 5 (decode_cubes), FP32 CUDA-core engine.
+// Reference: system/map.py:560-580 (get_sdf), :637-688 (do_meshing sampling), system/tracker.py:179-223
+// (compute_sdf_Hg), network/di_decoder.py:55-86, network/utility.py:61-126,129-149.
+#include <algorithm>
+
+#include "decoder_simt.cuh"
+
+namespace dfb {
+
+struct MapDev {
+  int nx, ny, nz;
+  float bx, by, bz, vs, inv_vs;
+  int div_mode;
+  float ignore_th;
+};
+
+static MapDev to_dev(const dfb_map_params* p) {
+  MapDev m;
+  m.nx = p->nx; m.ny = p->ny; m.nz = p->nz;
+  m.bx = p->bound_min[0]; m.by = p->bound_min[1]; m.bz = p->bound_min[2];
+  m.vs = p->voxel_size; m.inv_vs = 1.0f / p->voxel_size;
+  m.div_mode = p->div_mode; m.ignore_th = p->ignore_count_th;
+  return m;
+}
+
+// map.py:566-576.  The reference does not bounds-check (map.py:313); out-of-grid points are reported invalid here.
+__device__ __forceinline__ bool map_lookup(const MapDev& M, float px, float py, float pz, const int64_t* __restrict__ indexer,
+                                           const float* __restrict__ obs_count, long long& slot, float rel[3]) {
+  const float xn = div_vs(__fsub_rn(px, M.bx), M.vs, M.inv_vs, M.div_mode);
+  const float yn = div_vs(__fsub_rn(py, M.by), M.vs, M.inv_vs, M.div_mode);
+  const float zn = div_vs(__fsub_rn(pz, M.bz), M.vs, M.inv_vs, M.div_mode);
+  const float cx = ceilf(xn) - 1.0f, cy = ceilf(yn) - 1.0f, cz = ceilf(zn) - 1.0f;   // exact in fp32 for grid-sized values
+  if (!(cx >= 0.f && cx < (float)M.nx && cy >= 0.f && cy < (float)M.ny && cz >= 0.f && cz < (float)M.nz)) return false;
+  const long long lin = (long long)cz + (long long)M.nz * (long long)cy + (long long)M.nz * M.ny * (long long)cx;
+  slot = indexer[lin];
+  if (slot < 0) return false;
+  if (!(obs_count[slot] > M.ignore_th)) return false;
+  rel[0] = __fsub_rn(__fsub_rn(xn, cx), 0.5f);
+  rel[1] = __fsub_rn(__fsub_rn(yn, cy), 0.5f);
+  rel[2] = __fsub_rn(__fsub_rn(zn, cz), 0.5f);
+  return true;
+}
+
+__device__ __forceinline__ void load_query(DecSmem& S, const float* __restrict__ latent_row, const float rel[3], bool valid) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < DFB_LATENT_DIM; ++k) S.x0[k * DEC_T + tid] = valid ? __ldg(latent_row + k) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) S.x0[(DFB_LATENT_DIM + k) * DEC_T + tid] = valid ? rel[k] : 0.f;
+}
+
+extern __shared__ __align__(16) unsigned char dec_smem_raw[];
+
+// ------------------------------------------------------------------------------------------------
+// explicit rows: forward_model(network_input)  (utility.py:61)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_T, 1) decoder_explicit_kernel(const float* __restrict__ x, int n, const float* __restrict__ blob,
+                                                                    float* __restrict__ sdf, float* __restrict__ std_) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  for (int base = blockIdx.x * DEC_T; base < n; base += gridDim.x * DEC_T) {
+    const int i = base + tid;
+    for (int k = 0; k < DEC_IN; ++k) S.x0[k * DEC_T + tid] = i < n ? x[(size_t)i * DEC_IN + k] : 0.f;
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    if (i < n) {
+      sdf[i] = tanhf(z);
+      std_[i] = 0.05f + 0.5f * softplus_torch(u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_sdf (+ optional vector-Jacobian product for autograd)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_T, 1) get_sdf_kernel(MapDev M, const float* __restrict__ xyz, int n,
+                                                           const int64_t* __restrict__ indexer, const float* __restrict__ latents,
+                                                           const float* __restrict__ obs_count, const float* __restrict__ blob,
+                                                           float* __restrict__ sdf, float* __restrict__ std_, uint8_t* __restrict__ valid_out,
+                                                           const float* __restrict__ g_sdf, const float* __restrict__ g_std,
+                                                           float* __restrict__ grad_xyz) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  for (int base = blockIdx.x * DEC_T; base < n; base += gridDim.x * DEC_T) {
+    const int i = base + tid;
+    bool valid = false;
+    long long slot = -1;
+    float rel[3] = {0.f, 0.f, 0.f};
+    if (i < n) valid = map_lookup(M, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], indexer, obs_count, slot, rel);
+    load_query(S, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    const float s = tanhf(z);
+    const float sd = 0.05f + 0.5f * softplus_torch(u);
+    if (i < n) {
+      valid_out[i] = valid ? 1 : 0;
+      if (sdf) sdf[i] = valid ? s : 0.f;
+      if (std_) std_[i] = valid ? sd : 0.f;
+    }
+    if (grad_xyz) {   // uniform across the grid
+      float gs = 0.f, gu = 0.f;
+      if (valid) {
+        gs = g_sdf ? g_sdf[i] * (1.0f - s * s) : 0.f;
+        // d softplus(u)/du = sigmoid(u) (1 past the threshold)
+        const float dsp = u > 20.f ? 1.0f : 1.0f / (1.0f + expf(-u));
+        gu = g_std ? g_std[i] * 0.5f * dsp : 0.f;
+      }
+      float g[3];
+      decoder_backward_tile(S, blob, gs, gu, g);
+      if (i < n) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) grad_xyz[3 * (size_t)i + a] = valid ? div_vs(g[a], M.vs, M.inv_vs, M.div_mode) : 0.f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_sdf_Hg fused
+// ------------------------------------------------------------------------------------------------
+struct PoseDev {
+  float Rt[9], tt[3];   // total = last o delta
+  float Rd[9], td[3];   // delta
+  float Rl[9];          // last
+};
+
+__device__ __forceinline__ void xform(const float* R, const float* t, float x, float y, float z, float o[3]) {
+  // other @ R^T + t  (motion_util.py:323-328)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) o[j] = fmaf(z, R[3 * j + 2], fmaf(y, R[3 * j + 1], x * R[3 * j])) + t[j];
+}
+
+__global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
+                                                          const int64_t* __restrict__ indexer, const float* __restrict__ latents,
+                                                          const float* __restrict__ obs_count, const float* __restrict__ blob,
+                                                          int robust, float robust_k, int with_J, double* __restrict__ packed) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+  for (int base = blockIdx.x * DEC_T; base < n; base += gridDim.x * DEC_T) {
+    const int i = base + tid;
+    bool valid = false;
+    long long slot = -1;
+    float rel[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
+    if (i < n) {
+      pc[0] = obs[3 * (size_t)i]; pc[1] = obs[3 * (size_t)i + 1]; pc[2] = obs[3 * (size_t)i + 2];
+      float pw[3];
+      xform(P.Rt, P.tt, pc[0], pc[1], pc[2], pw);
+      valid = map_lookup(M, pw[0], pw[1], pw[2], indexer, obs_count, slot, rel);
+    }
+    load_query(S, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    const float s = tanhf(z);
+    const float sd = 0.05f + 0.5f * softplus_torch(u);
+    const float r = s / sd;                                   // tracker.py:191
+    float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (with_J) {
+      float g[3];
+      decoder_backward_tile(S, blob, valid ? (1.0f - s * s) / sd : 0.f, 0.f, g);
+      if (valid) {
+        float gw[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gw[a] = div_vs(g[a], M.vs, M.inv_vs, M.div_mode);
+        // Lai = grad @ R_last^T  (tracker.py:202-203): Lai_j = sum_k grad_k * R_last[j][k]
+#pragma unroll
+        for (int j = 0; j < 3; ++j) J[j] = fmaf(gw[2], P.Rl[3 * j + 2], fmaf(gw[1], P.Rl[3 * j + 1], gw[0] * P.Rl[3 * j]));
+        float d[3];
+        xform(P.Rd, P.td, pc[0], pc[1], pc[2], d);            // cur_dxyz (tracker.py:201)
+        J[3] = d[1] * J[2] - d[2] * J[1];                     // cross(cur_dxyz, Lai) (tracker.py:204)
+        J[4] = d[2] * J[0] - d[0] * J[2];
+        J[5] = d[0] * J[1] - d[1] * J[0];
+      }
+    }
+    if (valid) hg_accumulate(acc, J, r, robust_w(r, robust, robust_k), with_J != 0);
+  }
+  block_reduce_atomic<29, DEC_T>(acc, packed);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode_cubes
+// ------------------------------------------------------------------------------------------------
+// lattice coordinate of utility.get_samples minus the 0.5 network offset, fp32 op order of
+// `(idx * vsize + a) - 0.5` (utility.py:143-147, map.py:646-647)
+__device__ __forceinline__ float lattice(int i, float vsize, float a) {
+  return __fsub_rn(__fadd_rn(__fmul_rn((float)i, vsize), a), 0.5f);
+}
+
+// low-resolution pass: query id = b * r^3 + cell
+__global__ void __launch_bounds__(DEC_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ,
+                                                            int B, int r, float vsize, float a, const float* __restrict__ blob,
+                                                            float* __restrict__ low_sdf, float* __restrict__ low_std) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  const long long r3 = (long long)r * r * r;
+  const long long n = (long long)B * r3;
+  for (long long base = (long long)blockIdx.x * DEC_T; base < n; base += (long long)gridDim.x * DEC_T) {
+    const long long i = base + tid;
+    const bool valid = i < n;
+    float rel[3] = {0.f, 0.f, 0.f};
+    long long slot = 0;
+    if (valid) {
+      const int b = (int)(i / r3);
+      const int c = (int)(i - (long long)b * r3);
+      rel[0] = lattice(c / (r * r), vsize, a);
+      rel[1] = lattice((c / r) % r, vsize, a);
+      rel[2] = lattice(c % r, vsize, a);
+      slot = occ[b];
+    }
+    load_query(S, latents + slot * DFB_LATENT_DIM, rel, valid);
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    if (valid) {
+      low_sdf[i] = tanhf(z);
+      low_std[i] = 0.05f + 0.5f * softplus_torch(u);
+    }
+  }
+}
+
+// trilinear x2 with align_corners=True (F.interpolate, map.py:659-664), negate (map.py:688), and list the
+// |sdf| < band samples for exact re-decoding (map.py:668).
+__global__ void __launch_bounds__(256) cube_upsample_kernel(const float* __restrict__ low_sdf, const float* __restrict__ low_std,
+                                                            int B, int r, float band, float* __restrict__ cube_sdf,
+                                                            float* __restrict__ cube_std, int* __restrict__ refine_count,
+                                                            long long* __restrict__ refine_list) {
+  const int R = 2 * r;
+  const long long R3 = (long long)R * R * R;
+  const long long n = (long long)B * R3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (i < n) {
+    const int b = (int)(i / R3);
+    const int c = (int)(i - (long long)b * R3);
+    const int ix = c / (R * R), iy = (c / R) % R, iz = c % R;
+    const float scale = (float)(r - 1) / (float)(R - 1);        // area_pixel_compute_scale, align_corners
+    const float fx = scale * ix, fy = scale * iy, fz = scale * iz;
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const int x1 = x0 + (x0 < r - 1 ? 1 : 0), y1 = y0 + (y0 < r - 1 ? 1 : 0), z1 = z0 + (z0 < r - 1 ? 1 : 0);
+    const float lx1 = fx - x0, ly1 = fy - y0, lz1 = fz - z0;
+    const float lx0 = 1.f - lx1, ly0 = 1.f - ly1, lz0 = 1.f - lz1;
+    const float* ls = low_sdf + (long long)b * r * r * r;
+    const float* ld = low_std + (long long)b * r * r * r;
+#define AT(p, X, Y, Z) p[((X) * r + (Y)) * r + (Z)]
+    const float s = lx0 * (ly0 * (lz0 * AT(ls, x0, y0, z0) + lz1 * AT(ls, x0, y0, z1)) + ly1 * (lz0 * AT(ls, x0, y1, z0) + lz1 * AT(ls, x0, y1, z1))) +
+                    lx1 * (ly0 * (lz0 * AT(ls, x1, y0, z0) + lz1 * AT(ls, x1, y0, z1)) + ly1 * (lz0 * AT(ls, x1, y1, z0) + lz1 * AT(ls, x1, y1, z1)));
+    const float d = lx0 * (ly0 * (lz0 * AT(ld, x0, y0, z0) + lz1 * AT(ld, x0, y0, z1)) + ly1 * (lz0 * AT(ld, x0, y1, z0) + lz1 * AT(ld, x0, y1, z1))) +
+                    lx1 * (ly0 * (lz0 * AT(ld, x1, y0, z0) + lz1 * AT(ld, x1, y0, z1)) + ly1 * (lz0 * AT(ld, x1, y1, z0) + lz1 * AT(ld, x1, y1, z1)));
+#undef AT
+    cube_sdf[i] = -s;
+    cube_std[i] = d;
+    hit = fabsf(s) < band;
+  }
+  const int pos = warp_append(refine_count, hit);
+  if (hit) refine_list[pos] = i;
+}
+
+__global__ void __launch_bounds__(DEC_T, 1) cube_refine_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ,
+                                                               int r, float vsize, float a, const float* __restrict__ blob,
+                                                               const int* __restrict__ refine_count, const long long* __restrict__ refine_list,
+                                                               float* __restrict__ cube_sdf, float* __restrict__ cube_std) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  const int R = 2 * r;
+  const long long R3 = (long long)R * R * R;
+  const int n = *refine_count;
+  for (int base = blockIdx.x * DEC_T; base < n; base += gridDim.x * DEC_T) {
+    const int t = base + tid;
+    const bool valid = t < n;
+    float rel[3] = {0.f, 0.f, 0.f};
+    long long slot = 0, i = 0;
+    if (valid) {
+      i = refine_list[t];
+      const int b = (int)(i / R3);
+      const int c = (int)(i - (long long)b * R3);
+      rel[0] = lattice(c / (R * R), vsize, a);
+      rel[1] = lattice((c / R) % R, vsize, a);
+      rel[2] = lattice(c % R, vsize, a);
+      slot = occ[b];
+    }
+    load_query(S, latents + slot * DFB_LATENT_DIM, rel, valid);
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    if (valid) {
+      cube_sdf[i] = -tanhf(z);
+      cube_std[i] = 0.05f + 0.5f * softplus_torch(u);
+    }
+  }
+}
+
+template <typename K>
+static int set_dec_smem(K kernel) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
+  return DFB_OK;
+}
+
+static int dec_grid(long long n) { return (int)std::min<long long>(div_up(n, DEC_T), (long long)sm_count()); }
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+size_t dfb_decoder_blob_floats(void) { return DB_TOTAL; }
+
+int dfb_decoder_forward(const float* x, int n, const float* decoder_blob, float* sdf, float* std_, void* stream) {
+  DFB_CHECK_ARG(n >= 0, "decoder_forward");
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(x && decoder_blob && sdf && std_, "decoder_forward: null pointer");
+  int rc = set_dec_smem(decoder_explicit_kernel);
+  if (rc) return rc;
+  decoder_explicit_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), (cudaStream_t)stream>>>(x, n, decoder_blob, sdf, std_);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_get_sdf(const dfb_map_params* h_params, const float* xyz, int n, const int64_t* indexer, const float* latent_vecs,
+                const float* voxel_obs_count, const float* decoder_blob, float* sdf, float* std_, uint8_t* valid,
+                const float* g_sdf, const float* g_std, float* grad_xyz, void* stream) {
+  DFB_CHECK_ARG(h_params && n >= 0, "get_sdf");
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(xyz && indexer && latent_vecs && voxel_obs_count && decoder_blob && valid, "get_sdf: null pointer");
+  int rc = set_dec_smem(get_sdf_kernel);
+  if (rc) return rc;
+  get_sdf_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), (cudaStream_t)stream>>>(to_dev(h_params), xyz, n, indexer, latent_vecs,
+                                                                                voxel_obs_count, decoder_blob, sdf, std_, valid,
+                                                                                g_sdf, g_std, grad_xyz);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, const float* h_pose, const int64_t* indexer,
+               const float* latent_vecs, const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k,
+               int compute_J, double* out44, void* stream) {
+  DFB_CHECK_ARG(h_params && h_pose && out44 && n >= 0, "sdf_hg");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* packed = out44 + 44;                       // caller provides 80 doubles
+  DFB_CUDA(cudaMemsetAsync(out44, 0, sizeof(double) * 80, s));
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(obs_xyz && indexer && latent_vecs && voxel_obs_count && decoder_blob, "sdf_hg: null pointer");
+  PoseDev P;
+  for (int i = 0; i < 9; ++i) { P.Rt[i] = h_pose[i]; P.Rd[i] = h_pose[12 + i]; P.Rl[i] = h_pose[24 + i]; }
+  for (int i = 0; i < 3; ++i) { P.tt[i] = h_pose[9 + i]; P.td[i] = h_pose[21 + i]; }
+  int rc = set_dec_smem(sdf_hg_kernel);
+  if (rc) return rc;
+  sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count,
+                                                            decoder_blob, robust, robust_k, compute_J, packed);
+  launch_hg_expand(packed, out44, s);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+size_t dfb_decode_cubes_ws_bytes(int B, int r) {
+  Arena a(nullptr, 0);
+  size_t r3 = (size_t)r * r * r;
+  a.take<float>((size_t)B * r3 + 1); a.take<float>((size_t)B * r3 + 1); a.take<int>(4);
+  a.take<long long>((size_t)B * r3 * 8 + 1);
+  return a.off + 256;
+}
+
+int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r, float refine_band, const float* decoder_blob,
+                     float* cube_sdf, float* cube_std, void* ws, size_t ws_bytes, void* stream) {
+  DFB_CHECK_ARG(B >= 0 && r >= 2 && r <= 64, "decode_cubes");
+  if (B == 0) return DFB_OK;
+  DFB_CHECK_ARG(latent_vecs && occ && decoder_blob && cube_sdf && cube_std && ws, "decode_cubes: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena a(ws, ws_bytes);
+  const size_t r3 = (size_t)r * r * r;
+  float* low_sdf = a.take<float>((size_t)B * r3 + 1);
+  float* low_std = a.take<float>((size_t)B * r3 + 1);
+  int* refine_count = a.take<int>(4);
+  long long* refine_list = a.take<long long>((size_t)B * r3 * 8 + 1);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  // map.py:641-647: a = -(r//2)/r, b = 1 + ((r-1)//2)/r in Python doubles; vsize = (b-a)/(res-1) cast to fp32
+  const double sa = -(double)(r / 2) * (1.0 / r);
+  const double sb = 1.0 + (double)((r - 1) / 2) * (1.0 / r);
+  const float a32 = (float)sa;
+  const float v_low = (float)((sb - sa) / (r - 1));
+  const float v_high = (float)((sb - sa) / (2 * r - 1));
+  int rc = set_dec_smem(cube_low_kernel);
+  if (rc) return rc;
+  rc = set_dec_smem(cube_refine_kernel);
+  if (rc) return rc;
+  DFB_CUDA(cudaMemsetAsync(refine_count, 0, sizeof(int) * 4, s));
+  cube_low_kernel<<<dec_grid((long long)B * r3), DEC_T, sizeof(DecSmem), s>>>(latent_vecs, occ, B, r, v_low, a32, decoder_blob, low_sdf, low_std);
+  const long long nh = (long long)B * r3 * 8;
+  cube_upsample_kernel<<<div_up(nh, 256), 256, 0, s>>>(low_sdf, low_std, B, r, refine_band, cube_sdf, cube_std, refine_count, refine_list);
+  // the refine count lives on the device: launch a persistent grid that reads it
+  cube_refine_kernel<<<sm_count(), DEC_T, sizeof(DecSmem), s>>>(latent_vecs, occ, r, v_high, a32, decoder_blob, refine_count, refine_list,
+                                                                cube_sdf, cube_std);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // extern "C"

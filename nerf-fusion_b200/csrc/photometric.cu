@@ -1,0 +1,158 @@
+// Photometric term: Sobel gradients, per-pixel residual/Jacobian (drop-in ops) and the fused H/g reduction.
+// Reference: system/ext/imgproc/photometric.cu:3-138, system/tracker.py:136-177.
+#include "common.cuh"
+
+namespace dfb {
+
+__global__ void __launch_bounds__(256) gradient_xy_kernel(const float* __restrict__ I, int H, int W, float* __restrict__ g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int v = i / W, u = i - v * W;
+  if (v < 1 || v > H - 2 || u < 1 || u > W - 2) {
+    g[2 * i] = g[2 * i + 1] = CUDART_NAN_F;
+    return;
+  }
+  const float* r0 = I + (size_t)(v - 1) * W + u;
+  const float* r1 = I + (size_t)v * W + u;
+  const float* r2 = I + (size_t)(v + 1) * W + u;
+  float u_d1 = r0[1] - r0[-1], u_d2 = r1[1] - r1[-1], u_d3 = r2[1] - r2[-1];
+  g[2 * i] = (u_d1 + 2 * u_d2 + u_d3) / 8.0f;
+  float v_d1 = r2[-1] - r0[-1], v_d2 = r2[0] - r0[0], v_d3 = r2[1] - r0[1];
+  g[2 * i + 1] = (v_d1 + 2 * v_d2 + v_d3) / 8.0f;
+}
+
+struct RgbParams {
+  float k[9];
+  float kt[3];
+  float fx, fy, cx, cy;
+  float min_grad_scale, max_depth_delta;
+};
+
+// photometric.cu:24-77 for one pixel.  Returns validity; f and J[6] filled when valid.
+__device__ __forceinline__ bool rgb_pixel(const float* __restrict__ prev_I, const float* __restrict__ prev_D,
+                                          const float* __restrict__ cur_I, const float* __restrict__ cur_D,
+                                          const float* __restrict__ dIdxy, int H, int W, const RgbParams& P, int v, int u,
+                                          bool want_J, float& f, float* J) {
+  int i = v * W + u;
+  float dI_dx = dIdxy[2 * i], dI_dy = dIdxy[2 * i + 1];
+  float mTwo = (dI_dx * dI_dx) + (dI_dy * dI_dy);
+  if (mTwo < P.min_grad_scale || isnan(mTwo)) return false;
+  float d1 = cur_D[i];
+  if (isnan(d1)) return false;
+  float warpped_d1 = d1 * (P.k[6] * u + P.k[7] * v + P.k[8]) + P.kt[2];
+  int u0 = __float2int_rn((d1 * (P.k[0] * u + P.k[1] * v + P.k[2]) + P.kt[0]) / warpped_d1);
+  int v0 = __float2int_rn((d1 * (P.k[3] * u + P.k[4] * v + P.k[5]) + P.kt[1]) / warpped_d1);
+  if (!(u0 >= 0 && u0 < W && v0 >= 0 && v0 < H)) return false;
+  float d0 = prev_D[v0 * W + u0];
+  if (!(!isnan(d0) && fabsf(warpped_d1 - d0) <= P.max_depth_delta && d0 > 0.0f)) return false;
+  f = cur_I[i] - prev_I[v0 * W + u0];
+  if (want_J) {
+    float Gx = d0 * (u0 - P.cx) / P.fx, Gy = d0 * (v0 - P.cy) / P.fy, Gz = d0;
+    float p0 = dI_dx * P.fx / Gz;
+    float p1 = dI_dy * P.fy / Gz;
+    float p2 = -(p0 * Gx + p1 * Gy) / Gz;
+    J[0] = p0; J[1] = p1; J[2] = p2;
+    J[3] = -Gz * p1 + Gy * p2;
+    J[4] = Gz * p0 - Gx * p2;
+    J[5] = -Gy * p0 + Gx * p1;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) rgb_odometry_kernel(const float* prev_I, const float* prev_D, const float* cur_I,
+                                                           const float* cur_D, const float* dIdxy, int H, int W, RgbParams P,
+                                                           float* __restrict__ f_out, float* __restrict__ J_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int v = i / W, u = i - v * W;
+  float f, J[6];
+  bool ok = rgb_pixel(prev_I, prev_D, cur_I, cur_D, dIdxy, H, W, P, v, u, J_out != nullptr, f, J);
+  f_out[i] = ok ? f : CUDART_NAN_F;
+  if (J_out && ok) {           // the reference leaves J uninitialised where f is NaN; we do the same (never read)
+#pragma unroll
+    for (int a = 0; a < 6; ++a) J_out[6 * (size_t)i + a] = J[a];
+  }
+}
+
+constexpr int HG_T = 256;
+constexpr int HG_PIX_PER_THREAD = 4;
+
+__global__ void __launch_bounds__(HG_T) rgb_hg_kernel(const float* prev_I, const float* prev_D, const float* cur_I,
+                                                      const float* cur_D, const float* dIdxy, int H, int W, RgbParams P,
+                                                      int robust, float robust_k, int with_J, double* out29) {
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+  int base = blockIdx.x * (HG_T * HG_PIX_PER_THREAD) + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < HG_PIX_PER_THREAD; ++e) {
+    int i = base + e * HG_T;
+    if (i < H * W) {
+      int v = i / W, u = i - v * W;
+      float f, J[6];
+      if (rgb_pixel(prev_I, prev_D, cur_I, cur_D, dIdxy, H, W, P, v, u, with_J != 0, f, J)) {
+        if (with_J) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) J[a] = -J[a];   // tracker.py:162
+        }
+        hg_accumulate(acc, J, f, robust_w(f, robust, robust_k), with_J != 0);
+      }
+    }
+  }
+  block_reduce_atomic<29, HG_T>(acc, out29);
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+static void fill_rgb_params(RgbParams& P, const float* intr, const float* k, const float* kt, float mgs, float mdd) {
+  for (int i = 0; i < 9; ++i) P.k[i] = k[i];
+  for (int i = 0; i < 3; ++i) P.kt[i] = kt[i];
+  P.fx = intr[0]; P.fy = intr[1]; P.cx = intr[2]; P.cy = intr[3];
+  P.min_grad_scale = mgs; P.max_depth_delta = mdd;
+}
+
+extern "C" {
+
+int dfb_gradient_xy(const float* intensity, int H, int W, float* grad, void* stream) {
+  DFB_CHECK_ARG(H >= 0 && W >= 0, "gradient_xy");
+  if (H * W == 0) return DFB_OK;
+  DFB_CHECK_ARG(intensity && grad, "gradient_xy: null pointer");
+  gradient_xy_kernel<<<div_up((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(intensity, H, W, grad);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_rgb_odometry(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D,
+                     const float* cur_dIdxy, int H, int W, const float* h_intr, const float* h_krkinv,
+                     const float* h_kt, float min_grad_scale, float max_depth_delta, float* f, float* J, void* stream) {
+  DFB_CHECK_ARG(H > 0 && W > 0 && prev_I && prev_D && cur_I && cur_D && cur_dIdxy && h_intr && h_krkinv && h_kt && f,
+                "rgb_odometry");
+  RgbParams P;
+  fill_rgb_params(P, h_intr, h_krkinv, h_kt, min_grad_scale, max_depth_delta);
+  rgb_odometry_kernel<<<div_up((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(prev_I, prev_D, cur_I, cur_D,
+                                                                                      cur_dIdxy, H, W, P, f, J);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_rgb_hg(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D, const float* cur_dIdxy,
+               int H, int W, const float* h_intr, const float* h_krkinv, const float* h_kt, float min_grad_scale,
+               float max_depth_delta, int robust, float robust_k, int compute_J, double* out44, void* stream) {
+  DFB_CHECK_ARG(H > 0 && W > 0 && prev_I && prev_D && cur_I && cur_D && cur_dIdxy && h_intr && h_krkinv && h_kt && out44,
+                "rgb_hg");
+  cudaStream_t s = (cudaStream_t)stream;
+  RgbParams P;
+  fill_rgb_params(P, h_intr, h_krkinv, h_kt, min_grad_scale, max_depth_delta);
+  // out44 doubles as scratch: packed sums live in out44[44..72] (caller provides 80 doubles)
+  double* packed = out44 + 44;
+  DFB_CUDA(cudaMemsetAsync(out44, 0, sizeof(double) * 80, s));
+  rgb_hg_kernel<<<div_up((long long)H * W, HG_T * HG_PIX_PER_THREAD), HG_T, 0, s>>>(
+      prev_I, prev_D, cur_I, cur_D, cur_dIdxy, H, W, P, robust, robust_k, compute_J, packed);
+  launch_hg_expand(packed, out44, s);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // extern "C"

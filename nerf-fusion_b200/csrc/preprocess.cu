@@ -1,0 +1,622 @@
+// Stage 1: depth unprojection, uniform-grid exact neighbour search (radius-outlier filter, PCA normals),
+// 2 cm box filter / scatter_mean, groupby_sum.
+//
+// The reference builds a FLANN kd-tree TWICE per frame with thrust sorts and a host sync per tree level
+// (cuda_kdtree.cu:723-856) and keeps per-query heaps in global memory (cuda_kdtree.cu:130-214).  Both of its
+// queries are radius-bounded (pcproc.cu:104,120), so an exact answer only needs the points of the 27 cells
+// around the query in a uniform grid with cell >= radius: one counting sort, no host sync, candidates read
+// coalesced from the cell-sorted copy, result set in registers.
+#include "common.cuh"
+
+namespace dfb {
+
+// ------------------------------------------------------------------------------------------------
+// unproject (imgproc.cu:5-23).  x -> column (coalesced); the reference maps threadIdx.x to rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict__ depth, int H, int W, float fx,
+                                                        float fy, float cx, float cy, float* __restrict__ pc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int v = i / W, u = i - v * W;
+  float d = depth[i];
+  float x, y, z;
+  if (!isnan(d)) {
+    x = ((float)u - cx) / fx * d;   // same expression shape as imgproc.cu:17-19 (IEEE divide)
+    y = ((float)v - cy) / fy * d;
+    z = d;
+  } else {
+    x = y = z = CUDART_NAN_F;
+  }
+  pc[3 * i + 0] = x;
+  pc[3 * i + 1] = y;
+  pc[3 * i + 2] = z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// uniform grid
+// ------------------------------------------------------------------------------------------------
+constexpr int GRID_CAP = 1 << 20;  // max cells
+
+struct GridParams {
+  float ox, oy, oz, cell, inv_cell;
+  int nx, ny, nz, ncell;
+};
+
+struct GridWs {
+  unsigned* bbox;      // 6: min xyz, max xyz (ordered-uint encoding)
+  GridParams* gp;
+  int* cell_of;        // n
+  int* cell_count;     // GRID_CAP (+1)
+  int* cell_start;     // GRID_CAP + 1
+  int* block_sums;
+  float4* sorted;      // n   (x, y, z, original index bits)
+};
+
+static size_t grid_ws_layout(Arena& a, int n, GridWs* w) {
+  w->bbox = a.take<unsigned>(8);
+  w->gp = a.take<GridParams>(1);
+  w->cell_of = a.take<int>(n > 0 ? n : 1);
+  w->cell_count = a.take<int>(GRID_CAP + 1);
+  w->cell_start = a.take<int>(GRID_CAP + 1);
+  w->block_sums = a.take<int>(GRID_CAP / 2048 + 8);
+  w->sorted = a.take<float4>(n > 0 ? n : 1);
+  return a.off;
+}
+
+__global__ void bbox_init_kernel(unsigned* bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, int n, int stride, unsigned* bbox) {
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = p[(size_t)i * stride + a];
+      if (isfinite(v)) { mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (mn[a] <= mx[a]) {
+        atomicMin(&bbox[a], f2ord(mn[a]));
+        atomicMax(&bbox[3 + a], f2ord(mx[a]));
+      }
+    }
+  }
+}
+
+__global__ void grid_params_kernel(const unsigned* bbox, float radius, GridParams* gp) {
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = ord2f(bbox[a]);
+    hi[a] = ord2f(bbox[3 + a]);
+    if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
+  }
+  float cell = radius * 1.001f;
+  int nx, ny, nz;
+  for (int it = 0; it < 64; ++it) {
+    nx = (int)floorf((hi[0] - lo[0]) / cell) + 1;
+    ny = (int)floorf((hi[1] - lo[1]) / cell) + 1;
+    nz = (int)floorf((hi[2] - lo[2]) / cell) + 1;
+    if ((double)nx * ny * nz <= (double)GRID_CAP) break;
+    cell *= 1.25f;
+  }
+  gp->ox = lo[0]; gp->oy = lo[1]; gp->oz = lo[2];
+  gp->cell = cell; gp->inv_cell = 1.0f / cell;
+  gp->nx = nx; gp->ny = ny; gp->nz = nz; gp->ncell = nx * ny * nz;
+}
+
+__device__ __forceinline__ int3 cell_coord(const GridParams& g, float x, float y, float z) {
+  int cx = (int)floorf((x - g.ox) * g.inv_cell), cy = (int)floorf((y - g.oy) * g.inv_cell),
+      cz = (int)floorf((z - g.oz) * g.inv_cell);
+  cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+  return make_int3(cx, cy, cz);
+}
+
+__global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict__ pc4, int n, const GridParams* gpp,
+                                                         int* cell_of, int* cell_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GridParams g = *gpp;
+  float4 p = reinterpret_cast<const float4*>(pc4)[i];
+  int3 c = cell_coord(g, p.x, p.y, p.z);
+  int id = (c.x * g.ny + c.y) * g.nz + c.z;
+  cell_of[i] = id;
+  atomicAdd(&cell_count[id], 1);
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restrict__ pc4, int n, const int* cell_of,
+                                                           const int* cell_start, int* cursor, float4* sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = reinterpret_cast<const float4*>(pc4)[i];
+  int c = cell_of[i];
+  int pos = cell_start[c] + atomicAdd(&cursor[c], 1);
+  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+// squared distance, same expression shape as cutil_math.h:1127-1130 on (a - b) with w = 0
+__device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = ax - bx, dy = ay - by, dz = az - bz;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restrict__ sorted, int n,
+                                                           const GridParams* gpp, const int* __restrict__ cell_start,
+                                                           int nb_points, float radius, uint8_t* __restrict__ mask) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  GridParams g = *gpp;
+  float4 q = sorted[j];
+  int3 c = cell_coord(g, q.x, q.y, q.z);
+  const float r2 = radius * radius;
+  int count = 0;
+  for (int dx = -1; dx <= 1 && count < nb_points; ++dx) {
+    int x = c.x + dx;
+    if (x < 0 || x >= g.nx) continue;
+    for (int dy = -1; dy <= 1 && count < nb_points; ++dy) {
+      int y = c.y + dy;
+      if (y < 0 || y >= g.ny) continue;
+      int z0 = max(c.z - 1, 0), z1 = min(c.z + 1, g.nz - 1);
+      int row = (x * g.ny + y) * g.nz;
+      int b = cell_start[row + z0], e = cell_start[row + z1 + 1];   // z-neighbours are contiguous in memory
+      for (int k = b; k < e; ++k) {
+        float4 p = sorted[k];
+        // element - query, like cuda_kdtree.cu:1019 distance.dist(elements[i], q)
+        count += (dist2(p.x, p.y, p.z, q.x, q.y, q.z) < r2) ? 1 : 0;
+      }
+    }
+  }
+  mask[__float_as_int(q.w)] = count >= nb_points ? 1 : 0;
+}
+
+// pcproc.cu:21-96, same expression shapes (including the double-precision promotions through M_PI).
+__device__ float4 sym3eig_smallest(float3 x1, float3 x2, float3 x3) {
+  float4 ret;
+  const float p1 = x1.y * x1.y + x1.z * x1.z + x2.z * x2.z;
+  const float q = (x1.x + x2.y + x3.z) / 3.0f;
+  const float p2 = (x1.x - q) * (x1.x - q) + (x2.y - q) * (x2.y - q) + (x3.z - q) * (x3.z - q) + 2 * p1;
+  const float p = sqrtf(p2 / 6.0f);
+  const float ip = 1.0f / p;
+  const float b11 = ip * (x1.x - q), b12 = ip * x1.y, b13 = ip * x1.z;
+  const float b21 = ip * x2.x, b22 = ip * (x2.y - q), b23 = ip * x2.z;
+  const float b31 = ip * x3.x, b32 = ip * x3.y, b33 = ip * (x3.z - q);
+  float r = b11 * b22 * b33 + b12 * b23 * b31 + b13 * b21 * b32 - b13 * b22 * b31 - b12 * b21 * b33 - b11 * b23 * b32;
+  r = r / 2.0f;
+  float phi;
+  if (r <= -1) phi = (float)(3.14159265358979323846 / 3.0f);
+  else if (r >= 1) phi = 0;
+  else phi = acosf(r) / 3.0f;
+  ret.w = (float)(q + 2 * p * cos(phi + (2 * 3.14159265358979323846 / 3)));
+  x1.x -= ret.w; x2.y -= ret.w; x3.z -= ret.w;
+  const float r12_1 = x1.y * x2.z - x1.z * x2.y, r12_2 = x1.z * x2.x - x1.x * x2.z, r12_3 = x1.x * x2.y - x1.y * x2.x;
+  const float r13_1 = x1.y * x3.z - x1.z * x3.y, r13_2 = x1.z * x3.x - x1.x * x3.z, r13_3 = x1.x * x3.y - x1.y * x3.x;
+  const float r23_1 = x2.y * x3.z - x2.z * x3.y, r23_2 = x2.z * x3.x - x2.x * x3.z, r23_3 = x2.x * x3.y - x2.y * x3.x;
+  const float d1 = r12_1 * r12_1 + r12_2 * r12_2 + r12_3 * r12_3;
+  const float d2 = r13_1 * r13_1 + r13_2 * r13_2 + r13_3 * r13_3;
+  const float d3 = r23_1 * r23_1 + r23_2 * r23_2 + r23_3 * r23_3;
+  float d_max = d1;
+  int i_max = 0;
+  if (d2 > d_max) { d_max = d2; i_max = 1; }
+  if (d3 > d_max) { i_max = 2; }
+  if (i_max == 0) { float s = sqrtf(d1); ret.x = r12_1 / s; ret.y = r12_2 / s; ret.z = r12_3 / s; }
+  else if (i_max == 1) { float s = sqrtf(d2); ret.x = r13_1 / s; ret.y = r13_2 / s; ret.z = r13_3 / s; }
+  else { float s = sqrtf(d3); ret.x = r23_1 / s; ret.y = r23_2 / s; ret.z = r23_3 / s; }
+  return ret;
+}
+
+// K nearest (self included) kept sorted ascending in registers; then pcproc.cu:107-158.
+template <int K>
+__global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ sorted, int n, const GridParams* gpp,
+                                                      const int* __restrict__ cell_start, int max_nn, float radius,
+                                                      float3 cam, float* __restrict__ normals) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  GridParams g = *gpp;
+  float4 q = sorted[j];
+  int3 c = cell_coord(g, q.x, q.y, q.z);
+  float kd[K];
+  int ki[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { kd[t] = CUDART_INF_F; ki[t] = -1; }
+  const float r2 = radius * radius;
+  for (int dx = -1; dx <= 1; ++dx) {
+    int x = c.x + dx;
+    if (x < 0 || x >= g.nx) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      int y = c.y + dy;
+      if (y < 0 || y >= g.ny) continue;
+      int z0 = max(c.z - 1, 0), z1 = min(c.z + 1, g.nz - 1);
+      int row = (x * g.ny + y) * g.nz;
+      int b = cell_start[row + z0], e = cell_start[row + z1 + 1];
+      for (int k = b; k < e; ++k) {
+        float4 p = sorted[k];
+        float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+        // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
+        // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
+        if (d < r2 && d < kd[K - 1]) {
+          kd[K - 1] = d; ki[K - 1] = k;
+#pragma unroll
+          for (int t = K - 1; t > 0; --t) {
+            if (kd[t] < kd[t - 1]) {
+              float td = kd[t]; kd[t] = kd[t - 1]; kd[t - 1] = td;
+              int ti = ki[t]; ki[t] = ki[t - 1]; ki[t - 1] = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  int oi = __float_as_int(q.w);
+  float3 mean = make_float3(0.f, 0.f, 0.f);
+  float valid = 0.f;
+#pragma unroll
+  for (int t = 1; t < K; ++t) {
+    if (t < max_nn && kd[t] < r2) {
+      float4 p = sorted[ki[t]];
+      mean.x += p.x; mean.y += p.y; mean.z += p.z;
+      valid += 1.0f;
+    }
+  }
+  if (valid < 5.0f) {
+    normals[3 * oi + 0] = normals[3 * oi + 1] = normals[3 * oi + 2] = CUDART_NAN_F;
+    return;
+  }
+  mean.x /= valid; mean.y /= valid; mean.z /= valid;
+  float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
+#pragma unroll
+  for (int t = 1; t < K; ++t) {
+    if (t < max_nn && kd[t] < r2) {
+      float4 pp = sorted[ki[t]];
+      float3 pos = make_float3(pp.x - mean.x, pp.y - mean.y, pp.z - mean.z);
+      c1.x += pos.x * pos.x; c1.y += pos.x * pos.y; c1.z += pos.x * pos.z;
+      c2.x += pos.y * pos.x; c2.y += pos.y * pos.y; c2.z += pos.y * pos.z;
+      c3.x += pos.z * pos.x; c3.y += pos.z * pos.y; c3.z += pos.z * pos.z;
+    }
+  }
+  float4 ev = sym3eig_smallest(c1, c2, c3);
+  float3 nrm = make_float3(ev.x, ev.y, ev.z);
+  float3 dp = make_float3(q.x - cam.x, q.y - cam.y, q.z - cam.z);
+  if (nrm.x * dp.x + nrm.y * dp.y + nrm.z * dp.z > 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; }
+  normals[3 * oi + 0] = nrm.x;
+  normals[3 * oi + 1] = nrm.y;
+  normals[3 * oi + 2] = nrm.z;
+}
+
+static int build_grid(const float* pc4, int n, float radius, GridWs& w, cudaStream_t s) {
+  bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
+  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox);
+  grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, radius, w.gp);
+  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
+  grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count);
+  DFB_LAUNCH_CHECK();
+  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, GRID_CAP + 1, w.block_sums, nullptr, s);
+  if (rc) return rc;
+  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
+  grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter_mean / box filter: deterministic segmented mean
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seg_count_kernel(const int64_t* __restrict__ index64, const int* __restrict__ index32,
+                                                        int n, int* seg_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int g = index64 ? (int)index64[i] : index32[i];
+  atomicAdd(&seg_count[g], 1);
+}
+
+__global__ void __launch_bounds__(256) seg_fill_kernel(const int64_t* __restrict__ index64, const int* __restrict__ index32,
+                                                       int n, const int* seg_start, int* cursor, int* members) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int g = index64 ? (int)index64[i] : index32[i];
+  members[seg_start[g] + atomicAdd(&cursor[g], 1)] = i;
+}
+
+// One thread per output row: visit the segment's members in ascending row order (selection by repeated minimum;
+// segments are tiny) and sum sequentially -> bit-identical to a sequential CPU scatter (torch_scatter's CPU path).
+template <int D>
+__global__ void __launch_bounds__(128) seg_mean_kernel(const float* __restrict__ srcA, const float* __restrict__ srcB,
+                                                       const int* __restrict__ seg_start, const int* __restrict__ members,
+                                                       const int* __restrict__ n_out_dev, int n_out_host,
+                                                       float* __restrict__ outA, float* __restrict__ outB) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int n_out = n_out_dev ? *n_out_dev : n_out_host;
+  if (g >= n_out) return;
+  int b = seg_start[g], e = seg_start[g + 1];
+  float sa[D], sb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { sa[d] = 0.f; sb[d] = 0.f; }
+  int last = -1;
+  for (int t = b; t < e; ++t) {
+    int best = 0x7fffffff;
+    for (int u = b; u < e; ++u) {
+      int m = members[u];
+      if (m > last && m < best) best = m;
+    }
+    last = best;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      sa[d] += srcA[(size_t)best * D + d];
+      if (srcB) sb[d] += srcB[(size_t)best * D + d];
+    }
+  }
+  float cnt = (float)max(e - b, 1);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    outA[(size_t)g * D + d] = sa[d] / cnt;
+    if (srcB) outB[(size_t)g * D + d] = sb[d] / cnt;
+  }
+}
+
+// generic-D fallback (one thread per (row, column))
+__global__ void __launch_bounds__(128) seg_mean_generic_kernel(const float* __restrict__ src, int D,
+                                                               const int* __restrict__ seg_start,
+                                                               const int* __restrict__ members, int n_out,
+                                                               float* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out * D) return;
+  int g = t / D, d = t - g * D;
+  int b = seg_start[g], e = seg_start[g + 1];
+  float s = 0.f;
+  int last = -1;
+  for (int k = b; k < e; ++k) {
+    int best = 0x7fffffff;
+    for (int u = b; u < e; ++u) {
+      int m = members[u];
+      if (m > last && m < best) best = m;
+    }
+    last = best;
+    s += src[(size_t)best * D + d];
+  }
+  out[t] = s / (float)max(e - b, 1);
+}
+
+// box filter front end (tracker.py:16-21)
+struct BoxParams {
+  float mnx, mny, mnz;
+  long long nx, ny, nz;
+  int n_words;
+  int overflow;
+};
+constexpr long long BOX_BITS_CAP = 1ll << 27;  // 16 MiB bitmap
+
+__global__ void box_params_kernel(const unsigned* bbox, float voxel_size, int div_mode, BoxParams* bp) {
+  // min_bound = min - vs*0.5, max_bound = max + vs*0.5 (fp32 tensors; vs*0.5 is a Python double rounded to fp32)
+  float half = (float)((double)voxel_size * 0.5);
+  float inv = 1.0f / voxel_size;
+  float mn[3], ext[3];
+  for (int a = 0; a < 3; ++a) {
+    float lo = ord2f(bbox[a]), hi = ord2f(bbox[3 + a]);
+    mn[a] = __fsub_rn(lo, half);
+    float mx = __fadd_rn(hi, half);
+    ext[a] = floorf(div_vs(__fsub_rn(mx, mn[a]), voxel_size, inv, div_mode));
+  }
+  bp->mnx = mn[0]; bp->mny = mn[1]; bp->mnz = mn[2];
+  bp->nx = (long long)ext[0] + 16; bp->ny = (long long)ext[1] + 16; bp->nz = (long long)ext[2] + 16;
+  long long bits = bp->nx * bp->ny * bp->nz;
+  bp->overflow = bits > BOX_BITS_CAP ? 1 : 0;
+  if (bp->overflow) bits = 0;
+  bp->n_words = (int)((bits + 31) / 32);
+}
+
+__global__ void __launch_bounds__(256) box_key_kernel(const float* __restrict__ pts, int n, float voxel_size,
+                                                      int div_mode, const BoxParams* bpp, long long* keys,
+                                                      uint32_t* bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  BoxParams bp = *bpp;
+  if (bp.overflow) return;
+  float inv = 1.0f / voxel_size;
+  long long cx = (long long)floorf(div_vs(__fsub_rn(pts[3 * i + 0], bp.mnx), voxel_size, inv, div_mode));
+  long long cy = (long long)floorf(div_vs(__fsub_rn(pts[3 * i + 1], bp.mny), voxel_size, inv, div_mode));
+  long long cz = (long long)floorf(div_vs(__fsub_rn(pts[3 * i + 2], bp.mnz), voxel_size, inv, div_mode));
+  long long key = cx + cy * bp.nx + cz * bp.nx * bp.ny;   // tracker.py:20
+  if (key < 0 || key >= bp.nx * bp.ny * bp.nz) key = 0;   // non-finite input row; the reference would fault
+  keys[i] = key;
+  atomicOr(&bits[key >> 5], 1u << (key & 31));
+}
+
+__global__ void __launch_bounds__(256) box_rank_kernel(const long long* __restrict__ keys, int n,
+                                                       const uint32_t* __restrict__ bits, const int* __restrict__ word_rank,
+                                                       const BoxParams* bpp, int* rank_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (bpp->overflow) { rank_out[i] = 0; return; }
+  long long key = keys[i];
+  uint32_t w = bits[key >> 5];
+  rank_out[i] = word_rank[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
+}
+
+__global__ void box_finish_kernel(const BoxParams* bpp, int32_t* n_out) {
+  if (bpp->overflow) *n_out = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// groupby_sum (indexing.cu:59-71): one thread per element, coalesced reads, one red per element
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) groupby_sum_kernel(const float* __restrict__ values, const int64_t* __restrict__ indices,
+                                                          long long total, int L, int C, float* sum, int32_t* count) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int i = (int)(t / L), l = (int)(t - (long long)i * L);
+  long long g = indices[i];
+  if (g < 0 || g >= C) return;
+  atomicAdd(&sum[g * L + l], values[t]);
+  if (l == 0) atomicAdd(&count[g], 1);
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_unproject_depth(const float* depth, int H, int W, float fx, float fy, float cx, float cy, float* pc,
+                        void* stream) {
+  DFB_CHECK_ARG(depth && pc && H >= 0 && W >= 0, "unproject_depth");
+  if (H * W == 0) return DFB_OK;
+  unproject_kernel<<<div_up((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(depth, H, W, fx, fy, cx, cy, pc);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+size_t dfb_pcproc_ws_bytes(int n) {
+  Arena a(nullptr, 0);
+  GridWs w;
+  return grid_ws_layout(a, n, &w) + 256;
+}
+
+int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radius, uint8_t* mask, void* ws,
+                              size_t ws_bytes, void* stream) {
+  DFB_CHECK_ARG(n >= 0 && nb_points > 0 && radius > 0.f, "remove_radius_outlier");
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(pc4 && mask && ws, "remove_radius_outlier: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena a(ws, ws_bytes);
+  GridWs w;
+  grid_ws_layout(a, n, &w);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  int rc = build_grid(pc4, n, radius, w, s);
+  if (rc) return rc;
+  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, const float* h_cam_xyz, float* normals,
+                         void* ws, size_t ws_bytes, void* stream) {
+  DFB_CHECK_ARG(n >= 0 && max_nn > 1 && max_nn <= 32 && radius > 0.f && h_cam_xyz, "estimate_normals");
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(pc4 && normals && ws, "estimate_normals: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena a(ws, ws_bytes);
+  GridWs w;
+  grid_ws_layout(a, n, &w);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  int rc = build_grid(pc4, n, radius, w, s);
+  if (rc) return rc;
+  float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
+  if (max_nn <= 16)
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals);
+  else
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+size_t dfb_scatter_mean_ws_bytes(int n, int n_out) {
+  Arena a(nullptr, 0);
+  a.take<int>(n_out + 2); a.take<int>(n_out + 2); a.take<int>(n_out + 2); a.take<int>(n + 1);
+  a.take<int>(n_out / 2048 + 8);
+  return a.off + 256;
+}
+
+static int segmented_mean(const float* srcA, const float* srcB, const int64_t* index64, const int* index32, int n, int d,
+                          int n_out_cap, const int* n_out_dev, float* outA, float* outB, Arena& a, cudaStream_t s) {
+  int* seg_count = a.take<int>(n_out_cap + 2);
+  int* seg_start = a.take<int>(n_out_cap + 2);
+  int* cursor = a.take<int>(n_out_cap + 2);
+  int* members = a.take<int>(n + 1);
+  int* bsums = a.take<int>(n_out_cap / 2048 + 8);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  DFB_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int) * (n_out_cap + 2), s));
+  DFB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (n_out_cap + 2), s));
+  seg_count_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_count);
+  DFB_LAUNCH_CHECK();
+  int rc = exclusive_scan_i32(seg_count, seg_start, n_out_cap + 1, bsums, nullptr, s);
+  if (rc) return rc;
+  seg_fill_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_start, cursor, members);
+  if (d == 3)
+    seg_mean_kernel<3><<<div_up(n_out_cap, 128), 128, 0, s>>>(srcA, srcB, seg_start, members, n_out_dev, n_out_cap, outA, outB);
+  else {
+    seg_mean_generic_kernel<<<div_up((long long)n_out_cap * d, 128), 128, 0, s>>>(srcA, d, seg_start, members, n_out_cap, outA);
+    if (srcB) seg_mean_generic_kernel<<<div_up((long long)n_out_cap * d, 128), 128, 0, s>>>(srcB, d, seg_start, members, n_out_cap, outB);
+  }
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_scatter_mean(const float* src, const int64_t* index, int n, int d, int n_out, float* out, void* ws,
+                     size_t ws_bytes, void* stream) {
+  DFB_CHECK_ARG(n >= 0 && d > 0 && n_out >= 0, "scatter_mean");
+  if (n_out == 0) return DFB_OK;
+  DFB_CHECK_ARG(out && ws && (n == 0 || (src && index)), "scatter_mean: null pointer");
+  Arena a(ws, ws_bytes);
+  return segmented_mean(src, nullptr, index, nullptr, n, d, n_out, nullptr, out, nullptr, a, (cudaStream_t)stream);
+}
+
+size_t dfb_box_filter_ws_bytes(int n) {
+  Arena a(nullptr, 0);
+  a.take<unsigned>(8); a.take<BoxParams>(1); a.take<long long>(n + 1); a.take<uint32_t>(BOX_BITS_CAP / 32 + 1);
+  a.take<int>(BOX_BITS_CAP / 32 + 2); a.take<int>(BOX_BITS_CAP / 32 / 2048 + 8); a.take<int>(n + 1);
+  return a.off + dfb_scatter_mean_ws_bytes(n, n) + 256;
+}
+
+int dfb_point_box_filter(const float* points, const float* normals, int n, float voxel_size, int div_mode,
+                         float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  DFB_CHECK_ARG(n >= 0 && voxel_size > 0.f && d_n_out, "point_box_filter");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) { DFB_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), s)); return DFB_OK; }
+  DFB_CHECK_ARG(points && normals && out_points && out_normals && ws, "point_box_filter: null pointer");
+  Arena a(ws, ws_bytes);
+  unsigned* bbox = a.take<unsigned>(8);
+  BoxParams* bp = a.take<BoxParams>(1);
+  long long* keys = a.take<long long>(n + 1);
+  const int max_words = (int)(BOX_BITS_CAP / 32);
+  uint32_t* bits = a.take<uint32_t>(max_words + 1);
+  int* word_rank = a.take<int>(max_words + 2);
+  int* bsums = a.take<int>(max_words / 2048 + 8);
+  int* rank = a.take<int>(n + 1);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  // The bitmap is kept all-zero between calls (first use: the caller hands in zeroed memory or we clear it here
+  // once per call for the words a frame can touch -- we clear everything the key range may address).
+  bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
+  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(points, n, 3, bbox);
+  box_params_kernel<<<1, 1, 0, s>>>(bbox, voxel_size, div_mode, bp);
+  DFB_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)(max_words + 1), s));
+  box_key_kernel<<<div_up(n, 256), 256, 0, s>>>(points, n, voxel_size, div_mode, bp, keys, bits);
+  DFB_LAUNCH_CHECK();
+  int rc = exclusive_scan_popc(bits, word_rank, max_words, bsums, d_n_out, s);
+  if (rc) return rc;
+  box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank);
+  DFB_LAUNCH_CHECK();
+  rc = segmented_mean(points, normals, nullptr, rank, n, 3, n, d_n_out, out_points, out_normals, a, s);
+  if (rc) return rc;
+  box_finish_kernel<<<1, 1, 0, s>>>(bp, d_n_out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, int C, float* sum, int32_t* count,
+                    void* stream) {
+  DFB_CHECK_ARG(n >= 0 && L > 0 && C >= 0, "groupby_sum");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C == 0) return DFB_OK;
+  DFB_CHECK_ARG(sum && count, "groupby_sum: null output");
+  DFB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * (size_t)C * L, s));
+  DFB_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)C, s));
+  if (n == 0) return DFB_OK;
+  long long total = (long long)n * L;
+  groupby_sum_kernel<<<div_up(total, 256), 256, 0, s>>>(values, indices, total, L, C, sum, count);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // extern "C"

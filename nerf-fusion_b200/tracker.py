@@ -1,0 +1,205 @@
+"""SDFTracker: host-side mirror of system/tracker.py (preprocessing + Gauss-Newton over SDF and photometric terms).
+
+Same class/method names, arguments and return conventions as the reference.  What changed underneath:
+  * compute_sdf_Hg (tracker.py:179-223): ONE kernel (transform, map lookup, decoder forward + reverse pass, Jacobian,
+    robust weights, J^T J / J^T r / energy reduction) and ONE 352-byte device->host read, instead of ~40 torch ops,
+    an autograd tape, an (M,6,6) einsum tensor and 3 syncs;
+  * compute_rgb_Hg (tracker.py:136-177): the per-pixel residual/Jacobian kernel reduces in-kernel as well;
+  * preprocessing (tracker.py:89-120): unproject / radius filter / normals / box filter are the C-ABI ops.
+The 6x6 solve, pose composition and the accept/rollback logic stay on the host in float64, as in the reference.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from . import ext
+from ._lib import check, fptr
+from .ext import _p, _stream
+from .motion import Isometry
+
+import ctypes as C
+
+
+class FrameIntrinsic:
+    """dataset/production/__init__.py:4-18."""
+
+    def __init__(self, fx, fy, cx, cy, dscale=5000.0):
+        self.cx, self.cy, self.fx, self.fy, self.dscale = cx, cy, fx, fy, dscale
+
+    def to_K(self):
+        return np.asarray([[self.fx, 0.0, self.cx], [0.0, self.fy, self.cy], [0.0, 0.0, 1.0]])
+
+
+def _args_of(d):
+    import argparse
+    if isinstance(d, dict):
+        ns = argparse.Namespace()
+        ns.__dict__.update(d)
+        return ns
+    return d
+
+
+def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float, div_mode: int = 0):
+    """tracker.py:14-24 (unique + 2x scatter_mean fused into one deterministic segmented mean)."""
+    return ext.point_box_filter(points.contiguous(), normals.contiguous(), voxel_size, div_mode)
+
+
+_ROBUST = {None: 0, "huber": 1, "tukey": 2}
+
+
+class SDFTracker:
+    def __init__(self, map, args):
+        self.map = map
+        self.args = _args_of(args)
+        self.sdf_args = _args_of(self.args.sdf)
+        self.rgb_args = _args_of(self.args.rgb)
+        self.last_intensity = None
+        self.last_depth = None
+        self.all_pd_pose = []
+        self.last_processed_pc = None
+        self.cur_gt_pose = None
+        self.last_colored_pcd = None
+        self.n_unstable = 0
+        dev = map.device
+        self._hg_dev = torch.zeros((80,), dtype=torch.float64, device=dev)
+        self._hg_host = torch.zeros((80,), dtype=torch.float64).pin_memory()
+        self.n_sdf_evals = 0
+        self.n_rgb_evals = 0
+
+    # ------------------------------------------------------------------------------------------ preprocessing
+    def _make_image_pyramid(self, intensity_img, depth_img):
+        """tracker.py:42-57 (resampling is torch plumbing; gradients are the C-ABI op)."""
+        F = torch.nn.functional
+        d0_w, d0_h = intensity_img.size(1), intensity_img.size(0)
+        d1_w, d1_h = d0_w // 2, d0_h // 2
+        d2_w, d2_h = d1_w // 2, d1_h // 2
+        d0_i = intensity_img.view(1, 1, d0_h, d0_w)
+        d0_d = depth_img.view(1, 1, d0_h, d0_w)
+        d1_i = F.interpolate(d0_i, (d1_h, d1_w), mode="bilinear", align_corners=True)
+        d1_d = F.interpolate(d0_d, (d1_h, d1_w), mode="nearest")
+        d2_i = F.interpolate(d1_i, (d2_h, d2_w), mode="bilinear", align_corners=True)
+        d2_d = F.interpolate(d1_d, (d2_h, d2_w), mode="nearest")
+        Is = [t.squeeze(0).squeeze(0).contiguous() for t in (d0_i, d1_i, d2_i)]
+        Ds = [t.squeeze(0).squeeze(0).contiguous() for t in (d0_d, d1_d, d2_d)]
+        return Is, Ds, [ext.gradient_xy(t) for t in Is]
+
+    def preprocess_depth(self, depth_data, calib):
+        """tracker.py:89-120 (geometry half): returns (points (N,3), normals (N,3)) in camera space."""
+        pc_scale = self.sdf_args.subsample
+        pc_data = torch.nn.functional.interpolate(depth_data.unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
+                                                  recompute_scale_factor=False).squeeze(0).squeeze(0).contiguous()
+        pc_data = ext.unproject_depth(pc_data, calib.fx * pc_scale, calib.fy * pc_scale, calib.cx * pc_scale, calib.cy * pc_scale)
+        pc_data = torch.cat([pc_data, torch.zeros((pc_data.size(0), pc_data.size(1), 1), device=pc_data.device)], dim=-1)
+        pc_data = pc_data.reshape(-1, 4)
+        pc_data = pc_data[~torch.isnan(pc_data[..., 0])].contiguous()
+        with torch.cuda.device(self.map.device):
+            pc_data = pc_data[ext.remove_radius_outlier(pc_data, 16, 0.05)].contiguous()
+            normal_data = ext.estimate_normals(pc_data, 16, 0.1, [0.0, 0.0, 0.0])
+            ok = ~torch.isnan(normal_data[..., 0])
+            normal_data = normal_data[ok].contiguous()
+            pc_data = pc_data[ok, :3].contiguous()
+        return point_box_filter(pc_data, normal_data, 0.02, self.map.div_mode)
+
+    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False):
+        """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid."""
+        cur_intensity = torch.mean(rgb_data, dim=-1)
+        cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
+        pc_data, normal_data = self.preprocess_depth(cur_depth[0], calib)
+        self.last_processed_pc = [pc_data, normal_data]
+        if for_pc:
+            return self.last_processed_pc
+        if set_pose is not None:
+            final_pose = set_pose
+        else:
+            assert len(self.all_pd_pose) > 0
+            final_pose = self.gauss_newton(self.all_pd_pose[-1].dot(Isometry()), cur_intensity, cur_depth, cur_dIdxy, pc_data, calib)
+        self.last_intensity = cur_intensity
+        self.last_depth = cur_depth
+        self.all_pd_pose.append(final_pose)
+        return final_pose
+
+    # ------------------------------------------------------------------------------------------ GN terms
+    def _read_hg(self, scale_of_count):
+        """Copies the 44 result doubles to pinned host memory and unpacks (H, g, sum_wr2, count)."""
+        self._hg_host.copy_(self._hg_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = self._hg_host.numpy()
+        return v[:36].reshape(6, 6).copy(), v[36:42].copy(), float(v[42]), float(v[43])
+
+    def compute_rgb_Hg(self, pyramid_level, cur_delta_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, calib,
+                       no_grad=False):
+        """tracker.py:136-177."""
+        cur_R = cur_delta_pose.q.rotation_matrix
+        cur_t = cur_delta_pose.t
+        K = calib.to_K()
+        KRKinv = K @ cur_R @ np.linalg.inv(K)
+        Kt = K @ cur_t
+        ext.rgb_hg(self.last_intensity[pyramid_level], self.last_depth[pyramid_level], cur_intensity_pyramid[pyramid_level],
+                   cur_depth_pyramid[pyramid_level], cur_dIdxy_pyramid[pyramid_level], [calib.fx, calib.fy, calib.cx, calib.cy],
+                   KRKinv.flatten().tolist(), Kt.flatten().tolist(), self.rgb_args.min_grad_scale, self.rgb_args.max_depth_delta,
+                   _ROBUST[self.rgb_args.robust_kernel], self.rgb_args.robust_k, not no_grad, out=self._hg_dev)
+        self.n_rgb_evals += 1
+        H, g, e, cnt = self._read_hg(None)
+        error_scale = 1. / cnt * self.rgb_args.weight if cnt > 0 else float("nan")
+        if no_grad:
+            return None, None, float(e * error_scale)
+        return H * error_scale, g * error_scale, float(e * error_scale)
+
+    def compute_sdf_Hg(self, n_iter, last_pose, cur_delta_pose, obs_xyz, no_grad=False):
+        """tracker.py:179-223.  Returns (H (6,6) f64 | None, g (6,) f64 | None, energy float)."""
+        m = self.map
+        total = last_pose.dot(cur_delta_pose)
+        pose = np.concatenate([total.q.rotation_matrix.reshape(-1), total.t, cur_delta_pose.q.rotation_matrix.reshape(-1),
+                               cur_delta_pose.t, last_pose.q.rotation_matrix.reshape(-1)]).astype(np.float32)
+        obs = obs_xyz.contiguous()
+        with torch.cuda.device(m.device):
+            check(m.lib.dfb_sdf_hg(C.byref(m._params), _p(obs), obs.size(0), fptr(pose.tolist()), _p(m.indexer), _p(m.latent_vecs),
+                                   _p(m.voxel_obs_count), _p(m.decoder_blob), _ROBUST[self.sdf_args.robust_kernel],
+                                   float(self.sdf_args.robust_k), int(not no_grad), _p(self._hg_dev), _stream()))
+        self.n_sdf_evals += 1
+        H, g, e, cnt = self._read_hg(None)
+        error_scale = 1.0 / cnt if cnt > 0 else float("nan")
+        if no_grad:
+            return None, None, float(e * error_scale)
+        return H * error_scale, g * error_scale, float(e * error_scale)
+
+    # ------------------------------------------------------------------------------------------ Gauss-Newton
+    def gauss_newton(self, init_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz, calib):
+        """tracker.py:225-288 (control flow unchanged: rollback+break when the energy rises, one evaluation-only pass per
+        group, instability counter)."""
+        last_pose = self.all_pd_pose[-1]
+        cur_delta_pose = last_pose.inv().dot(init_pose)
+        last_delta_pose = copy.deepcopy(cur_delta_pose)
+        i_iter = 0
+        for group in self.args.iter_config:
+            last_energy = np.inf
+            for i_iter in list(range(group["n"])) + [-1]:
+                H = np.zeros((6, 6), dtype=float)
+                g = np.zeros((6,), dtype=float)
+                cur_energy = 0.0
+                for loss_config in group["type"]:
+                    if loss_config[0] == "sdf":
+                        tH, tg, te = self.compute_sdf_Hg(i_iter, last_pose, cur_delta_pose, obs_xyz, i_iter == -1)
+                    elif loss_config[0] == "rgb":
+                        tH, tg, te = self.compute_rgb_Hg(loss_config[1], cur_delta_pose, cur_intensity_pyramid, cur_depth_pyramid,
+                                                         cur_dIdxy_pyramid, calib, i_iter == -1)
+                    else:
+                        raise NotImplementedError(loss_config[0])     # 'motion' is referenced but undefined in the reference
+                    cur_energy += te
+                    if i_iter != -1:
+                        H += tH
+                        g += tg
+                if cur_energy > last_energy:
+                    cur_delta_pose = last_delta_pose
+                    break
+                last_delta_pose = copy.deepcopy(cur_delta_pose)
+                last_energy = cur_energy
+                if i_iter != -1:
+                    xi = np.linalg.solve(H, -g)
+                    cur_delta_pose = Isometry.from_twist(xi) @ cur_delta_pose
+        if i_iter >= 10:
+            self.n_unstable += 1
+            if self.n_unstable >= 3:
+                self.rgb_args.weight = max(self.rgb_args.weight, 500.)
+        return last_pose.dot(cur_delta_pose)

@@ -1,0 +1,93 @@
+"""Host-side weight folding and packing into the blobs the kernels read (layouts: csrc/decoder_simt.cuh DB_*,
+csrc/integrate.cu EB_*).
+
+Replaces network/utility.py:22-58 (load_model), the weight-norm recompute that runs on every decoder forward after
+fix_weight_norm_pickle (network/utility.py:211-220; W = g * v / ||v||_row) and eval-mode BatchNorm in the encoder
+(utils/pt_util.py:193-206), which is folded into the preceding 1x1 convolution.
+Checkpoint tensors keep the reference's key names with a 'dec.' / 'enc.' prefix.
+"""
+from pathlib import Path
+
+import numpy as np
+import torch
+
+
+def load_checkpoint(hyper_dir, epoch=300):
+    """Read ckpt/default/{model,encoder}_<epoch>.pth.tar (reference format: {'epoch', 'model_state'})."""
+    hyper_dir = Path(hyper_dir)
+    out = {}
+    sd = torch.load(hyper_dir / f"model_{epoch}.pth.tar", map_location="cpu", weights_only=False)["model_state"]
+    for k, v in sd.items():
+        out["dec." + k] = v.float()
+    se = torch.load(hyper_dir / f"encoder_{epoch}.pth.tar", map_location="cpu", weights_only=False)["model_state"]
+    for k, v in se.items():
+        out["enc." + k] = v.float() if v.is_floating_point() else v
+    return out
+
+
+def load_npz(path):
+    z = np.load(path)
+    return {k: torch.from_numpy(z[k].copy()) for k in z.files}
+
+
+def decoder_matrices(W):
+    """Effective (weight-normed) decoder matrices, fp32, computed like torch._weight_norm: v * (g / ||v||)."""
+    M = {}
+    for l in range(5):
+        v, g = W[f"dec.lin{l}.weight_v"].float(), W[f"dec.lin{l}.weight_g"].float()
+        M[f"W{l}"] = (v * (g / v.norm(dim=1, keepdim=True))).numpy()
+        M[f"b{l}"] = W[f"dec.lin{l}.bias"].float().numpy()
+    M["Wu"] = W["dec.uncertainty_layer.weight"].float().numpy()
+    M["bu"] = W["dec.uncertainty_layer.bias"].float().numpy()
+    return M
+
+
+def _pack_dense(mat):
+    """mat (n_in, n_out) -> chunks of 64 output columns, each stored [n_in][cw] row-major."""
+    n_in, n_out = mat.shape
+    parts = []
+    for c0 in range(0, n_out, 64):
+        parts.append(np.ascontiguousarray(mat[:, c0:min(c0 + 64, n_out)]).reshape(-1))
+    return np.concatenate(parts)
+
+
+def pack_decoder(W):
+    M = decoder_matrices(W)
+    W0, W1, W2, W3, W4 = M["W0"], M["W1"], M["W2"], M["W3"], M["W4"]
+    assert W0.shape == (128, 32) and W1.shape == (128, 128) and W2.shape == (96, 128) and W3.shape == (128, 128) and W4.shape == (1, 128)
+    parts = [
+        _pack_dense(W0.T), _pack_dense(W1.T), _pack_dense(W2.T), _pack_dense(W3.T),       # forward: [k][o]
+        _pack_dense(W3[:, :96]), _pack_dense(W2), _pack_dense(W1),                          # reverse: [o][k]
+    ]
+    small = np.zeros(1512, dtype=np.float32)
+    small[0:128] = M["b0"]; small[128:256] = M["b1"]; small[256:352] = M["b2"]; small[352:480] = M["b3"]
+    small[480:608] = W4[0]; small[608:736] = M["Wu"][0]
+    small[736:736 + 384] = W3[:, 125:128].reshape(-1)
+    small[1120:1120 + 384] = W0[:, 29:32].reshape(-1)
+    small[1504] = M["b4"][0]; small[1505] = M["bu"][0]
+    blob = np.concatenate(parts + [small]).astype(np.float32)
+    return blob
+
+
+def encoder_matrices(W):
+    """BN-folded encoder layers: list of (weight (out,in), bias (out,))."""
+    layers = []
+    for l in range(3):
+        w = W[f"enc.mlp.layer{l}.conv.weight"].float().squeeze(-1).double()
+        g = W[f"enc.mlp.layer{l}.normlayer.bn.weight"].double(); b = W[f"enc.mlp.layer{l}.normlayer.bn.bias"].double()
+        mu = W[f"enc.mlp.layer{l}.normlayer.bn.running_mean"].double(); var = W[f"enc.mlp.layer{l}.normlayer.bn.running_var"].double()
+        s = g / torch.sqrt(var + 1e-5)
+        layers.append(((w * s[:, None]).float().numpy(), (b - s * mu).float().numpy()))
+    layers.append((W["enc.mlp.layer3.conv.weight"].float().squeeze(-1).numpy(), W["enc.mlp.layer3.conv.bias"].float().numpy()))
+    return layers
+
+
+def pack_encoder(W):
+    (w0, b0), (w1, b1), (w2, b2), (w3, b3) = encoder_matrices(W)
+    assert w0.shape == (32, 6) and w1.shape == (64, 32) and w2.shape == (256, 64) and w3.shape == (29, 256)
+    p0 = np.zeros((32, 8), np.float32); p0[:, :6] = w0
+    p2 = np.ascontiguousarray(w2.reshape(32, 8, 64).transpose(0, 2, 1))            # [group][k][8]
+    p3 = np.zeros((256, 32), np.float32); p3[:, :29] = w3.T
+    pb3 = np.zeros(32, np.float32); pb3[:29] = b3
+    blob = np.concatenate([p0.reshape(-1), b0, w1.reshape(-1), b1, p2.reshape(-1), b2, p3.reshape(-1), pb3]).astype(np.float32)
+    return blob

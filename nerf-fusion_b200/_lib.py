@@ -61,6 +61,39 @@ SIGNATURES = {
     "dfb_marching_cubes": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
 }
 
+# kernels (and memset nodes excluded) each entry point launches; used for the bench's `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 6,
+    "dfb_point_box_filter": 14, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
+    "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
+    "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
+}
+CALLS = {}
+
+
+class _Api:
+    """Typed entry points; every call is counted in CALLS (name -> number of calls)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(cdll, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, self._counted(name, fn) if name in KERNELS_PER_CALL else fn)
+
+    @staticmethod
+    def _counted(name, fn):
+        def call(*a):
+            CALLS[name] = CALLS.get(name, 0) + 1
+            return fn(*a)
+        return call
+
+
+def kernel_launches():
+    return sum(KERNELS_PER_CALL[k] * v for k, v in CALLS.items())
+
+
 _lib = None
 
 
@@ -73,13 +106,8 @@ def load():
     if not path.exists():
         raise DfbError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        f"(nvcc, sm_100a).  difusion_b200 has no CPU fallback.")
-    lib = C.CDLL(str(path))
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the symbol is missing
-        fn.restype = res
-        fn.argtypes = args
-    _lib = lib
-    return lib
+    _lib = _Api(C.CDLL(str(path)))
+    return _lib
 
 
 def check(rc):

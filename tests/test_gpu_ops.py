@@ -1,0 +1,171 @@
+"""-m gpu: operator-level parity of the C-ABI ops (called through nerf-fusion_b200.ext) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, ops
+from util import pkg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _depth_frame(H=240, W=320, seed=0):
+    synth = pkg().synth
+    seq = synth.SyntheticSequence(n_frames=1, H=H, W=W, seed=seed)
+    d, rgb = seq.frame(0)
+    d = d.clone(); d[(d < 0.5) | (d > 5.0)] = float("nan")
+    return d, rgb, tuple(c * H / 480.0 for c in synth.ICL_CALIB)
+
+
+def _cloud(n_max=None):
+    d, _, calib = _depth_frame()
+    pc = ops.unproject_depth(d.numpy(), *calib).reshape(-1, 3)
+    pc = pc[~np.isnan(pc[:, 0])]
+    if n_max:
+        pc = pc[:n_max]
+    return np.concatenate([pc, np.zeros((pc.shape[0], 1), np.float32)], 1)
+
+
+def test_unproject_depth_bit_exact():
+    ext = pkg().ext
+    d, _, calib = _depth_frame()
+    got = ext.unproject_depth(d.to(DEV), *calib).cpu().numpy()
+    ref = ops.unproject_depth(d.numpy(), *calib)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    # empty input
+    assert ext.unproject_depth(torch.zeros((0, 8), device=DEV), 1, 1, 0, 0).shape == (0, 8, 3)
+
+
+def test_unproject_rejects_cpu_and_noncontiguous():
+    ext = pkg().ext
+    with pytest.raises(RuntimeError):
+        ext.unproject_depth(torch.zeros(4, 4), 1, 1, 0, 0)
+    with pytest.raises(RuntimeError):
+        ext.unproject_depth(torch.zeros(4, 8, device=DEV)[:, ::2], 1, 1, 0, 0)
+
+
+def test_remove_radius_outlier():
+    ext = pkg().ext
+    pc4 = _cloud()
+    got = ext.remove_radius_outlier(torch.from_numpy(pc4).to(DEV), 16, 0.05).cpu().numpy()
+    dist, _ = ops.knn(pc4, 16, max_radius=0.05)
+    ref = dist[:, 15] < np.float32(0.05) * np.float32(0.05)
+    r2 = np.float32(0.05) * np.float32(0.05)
+    border = np.abs(dist[:, 15] - r2) <= 4e-7 * r2            # FMA-contraction ulp band
+    assert np.array_equal(got[~border], ref[~border])
+    assert border.mean() < 1e-3
+    assert 0.05 < got.mean() < 1.0
+    # ragged / tiny inputs
+    assert ext.remove_radius_outlier(torch.zeros((0, 4), device=DEV), 16, 0.05).numel() == 0
+    few = torch.from_numpy(pc4[:5]).to(DEV)
+    assert not ext.remove_radius_outlier(few, 16, 0.05).any()
+
+
+def test_estimate_normals():
+    ext = pkg().ext
+    pc4 = _cloud()
+    keep = ops.remove_radius_outlier(pc4, 16, 0.05)
+    pc4 = pc4[keep]
+    got = ext.estimate_normals(torch.from_numpy(pc4).to(DEV), 16, 0.1, [0.0, 0.0, 0.0]).cpu().numpy()
+    ref = ops.estimate_normals(pc4, 16, 0.1, [0.0, 0.0, 0.0])
+    nan_g, nan_r = np.isnan(got[:, 0]), np.isnan(ref[:, 0])
+    assert (nan_g != nan_r).mean() < 1e-3
+    ok = ~nan_g & ~nan_r
+    err = np.abs(got[ok] - ref[ok]).max(1)
+    # ties in the 16-NN set / eigen-solver conditioning: allow a tiny tail, demand tight agreement elsewhere
+    assert np.quantile(err, 0.99) < 2e-3, np.quantile(err, [0.5, 0.9, 0.99, 1.0])
+    assert np.median(err) < 1e-5
+    assert abs(np.linalg.norm(got[ok], axis=1).mean() - 1.0) < 1e-3
+    assert ((got[ok] * pc4[ok, :3]).sum(1) <= 1e-6).all()       # oriented towards the camera at the origin
+
+
+def test_point_box_filter_bit_exact():
+    ext = pkg().ext
+    pc4 = _cloud()
+    rng = np.random.RandomState(0)
+    nrm = rng.randn(pc4.shape[0], 3).astype(np.float32)
+    gp, gn = ext.point_box_filter(torch.from_numpy(pc4[:, :3].copy()).to(DEV), torch.from_numpy(nrm).to(DEV), 0.02)
+    rp, rn, _ = ops.point_box_filter(pc4[:, :3], nrm, 0.02)
+    assert gp.shape[0] == rp.shape[0]
+    assert np.array_equal(gp.cpu().numpy(), rp)
+    assert np.array_equal(gn.cpu().numpy(), rn)
+    gp2, _ = ext.point_box_filter(torch.from_numpy(pc4[:, :3].copy()).to(DEV), torch.from_numpy(nrm).to(DEV), 0.02, 1)
+    rp2, _, _ = ops.point_box_filter(pc4[:, :3], nrm, 0.02, divide="recip")
+    assert np.array_equal(gp2.cpu().numpy(), rp2)
+
+
+def test_scatter_mean_and_groupby_sum():
+    ext = pkg().ext
+    rng = np.random.RandomState(3)
+    n, C = 20000, 700
+    idx = rng.randint(0, C, size=n).astype(np.int64)
+    idx[0] = C - 1
+    src = rng.randn(n, 3).astype(np.float32)
+    got = ext.scatter_mean(torch.from_numpy(src).to(DEV), torch.from_numpy(idx).to(DEV), dim=0).cpu().numpy()
+    assert np.array_equal(got, ops.scatter_mean(src, idx))
+    src7 = rng.randn(n, 7).astype(np.float32)
+    got7 = ext.scatter_mean(torch.from_numpy(src7).to(DEV), torch.from_numpy(idx).to(DEV)).cpu().numpy()
+    assert np.array_equal(got7, ops.scatter_mean(src7, idx))
+    vals = rng.randn(n, 29).astype(np.float32)
+    s, c = ext.groupby_sum(torch.from_numpy(vals).to(DEV), torch.from_numpy(idx).to(DEV), C)
+    rs, rc = ops.groupby_sum(vals, idx, C)
+    assert np.array_equal(c.cpu().numpy(), rc)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=1e-4, atol=1e-4)
+    s0, c0 = ext.groupby_sum(torch.zeros((0, 29), device=DEV), torch.zeros((0,), dtype=torch.long, device=DEV), 5)
+    assert s0.abs().sum() == 0 and c0.sum() == 0
+
+
+def test_gradient_xy_and_rgb_odometry():
+    ext = pkg().ext
+    synth = pkg().synth
+    seq = synth.SyntheticSequence(n_frames=2, H=240, W=320)
+    (d0, c0), (d1, c1) = seq.frame(0), seq.frame(1)
+    for d in (d0, d1):
+        d[(d < 0.5) | (d > 5.0)] = float("nan")
+    I0, I1 = c0.mean(-1).contiguous(), c1.mean(-1).contiguous()
+    g = ext.gradient_xy(I1.to(DEV)).cpu().numpy()
+    gr = ops.gradient_xy(I1.numpy())
+    assert np.array_equal(np.isnan(g), np.isnan(gr))
+    np.testing.assert_allclose(g[1:-1, 1:-1], gr[1:-1, 1:-1], rtol=0, atol=1e-7)
+    calib = [c * 0.5 for c in synth.ICL_CALIB]
+    K = np.array([[calib[0], 0, calib[2]], [0, calib[1], calib[3]], [0, 0, 1.0]])
+    from oracle.tracker_oracle import Pose
+    dp = Pose.from_twist(np.array([0.004, -0.002, 0.003, 0.001, -0.002, 0.0015]))
+    krk = (K @ dp.R @ np.linalg.inv(K)).flatten().tolist(); kt = (K @ dp.t).flatten().tolist()
+    f, J = ext.rgb_odometry(I0.to(DEV), d0.to(DEV), I1.to(DEV), d1.to(DEV), torch.from_numpy(gr).to(DEV), calib, krk, kt, 0.0, 0.2, True)
+    fr, Jr = ops.rgb_odometry(I0.numpy(), d0.numpy(), I1.numpy(), d1.numpy(), gr, calib, krk, kt, 0.0, 0.2, True)
+    f = f.cpu().numpy(); J = J.cpu().numpy()
+    both = ~np.isnan(f) & ~np.isnan(fr)
+    assert (np.isnan(f) != np.isnan(fr)).mean() < 2e-3          # rounding-boundary pixels (see oracle/ops.py)
+    same = both & (np.abs(f - fr) < 1e-6)
+    assert same.sum() > 0.995 * both.sum()
+    np.testing.assert_allclose(J[same], Jr[same], rtol=2e-4, atol=1e-4)
+    # fused reduction == reduction of the per-pixel outputs
+    out = ext.rgb_hg(I0.to(DEV), d0.to(DEV), I1.to(DEV), d1.to(DEV), torch.from_numpy(gr).to(DEV), calib, krk, kt, 0.0, 0.2, 0, 0.01, True)
+    out = out.cpu().numpy()
+    m = ~np.isnan(f)
+    Jm = -J[m].astype(np.float64); fm = f[m].astype(np.float64)
+    np.testing.assert_allclose(out[:36].reshape(6, 6), Jm.T @ Jm, rtol=1e-5)
+    np.testing.assert_allclose(out[36:42], Jm.T @ fm, rtol=1e-5, atol=1e-6 * np.abs(Jm.T @ fm).max())
+    np.testing.assert_allclose(out[42], (fm * fm).sum(), rtol=1e-5)
+    assert out[43] == m.sum()
+
+
+def test_encoder_and_decoder_forward(weights):
+    d = pkg()
+    rng = np.random.RandomState(5)
+    x = np.concatenate([rng.rand(5000, 3) - 0.5, rng.randn(5000, 3)], 1).astype(np.float32)
+    blob = torch.from_numpy(d.weights.pack_encoder(weights)).to(DEV)
+    got = d.ext.encoder_forward(torch.from_numpy(x).to(DEV), blob).cpu().numpy()
+    ref = nets.encoder_forward(weights, torch.from_numpy(x)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-5)
+    xq = np.concatenate([rng.randn(3001, 29) * 0.1, rng.rand(3001, 3) - 0.5], 1).astype(np.float32)
+    dblob = torch.from_numpy(d.weights.pack_decoder(weights)).to(DEV)
+    sdf, std = d.ext.decoder_forward(torch.from_numpy(xq).to(DEV), dblob)
+    rs, rd = nets.decoder_forward(weights, torch.from_numpy(xq))
+    np.testing.assert_allclose(sdf.cpu().numpy(), rs.numpy(), atol=2e-6)       # SDF tolerance: 1e-4 m = 1e-3 voxel units
+    np.testing.assert_allclose(std.cpu().numpy(), rd.numpy(), atol=2e-6)
+    s0, _ = d.ext.decoder_forward(torch.zeros((0, 32), device=DEV), dblob)
+    assert s0.numel() == 0

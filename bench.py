@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Headline benchmark: 640x480 depth frames/s integrated+tracked (BASELINE.json metric, configs[1]:
+ICL-NUIM-shaped synthetic sequence through the per-frame path main.py::refresh drives -- depth cut, SDFTracker.
+track_camera (preprocess + Gauss-Newton over SDF and photometric terms), integrate_keyframe every 20 frames --
+with configs/fusion-lr-kt.yaml + ckpt/default weights (tests/golden/weights.npz is a verbatim export).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one frame.  `value` = frames/s with the frames already resident in HBM; `e2e` = the same loop with the
+frames in pinned HOST memory, H2D copy of depth+rgb and D2H read of the pose-defining reductions inside the timed
+region.  N > 1 (torchrun): the tracked path does not shard (DESIGN.md "Multi-GPU": replicas only) -> every rank
+runs an independent replica on its own stream of frames, scaling "weak".
+`--impl reference`: the reference algorithm on the host cores (oracle port of system/map.py + system/tracker.py,
+all threads), each step a bounded sample of the same frame workload (see cpu_reference()).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "640x480 depth frames/sec integrated+tracked"
+UNIT = "frames/s"
+WORKLOAD = "ICL-NUIM-shaped synthetic 640x480 RGB-D sequence, fusion-lr-kt.yaml, integrate every 20 frames, resolution 4"
+FLOP_FWD, FLOP_FWD_BWD = 98816, 182528            # per decoder query
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm": d["hbm_gbs"], "bf16": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def make_system(dfb, device):
+    from util import MAPPING, TRACKING, ns, GOLD
+    W = dfb.weights.load_npz(GOLD / "weights.npz")
+    m = dfb.DenseIndexedMap(W, ns(dict(MAPPING)), 29, torch.device(device))
+    trk = dfb.SDFTracker(m, ns(dict(TRACKING)))
+    return m, trk
+
+
+def gen_frames(dfb, n, device, seed):
+    seq = dfb.synth.SyntheticSequence(n_frames=n, device=device, seed=seed)
+    return [seq.frame(i) for i in range(n)], seq
+
+
+def refresh(dfb, m, trk, frame_id, depth, rgb, calib, first_iso, integrate_interval=20, depth_cut=(0.5, 5.0)):
+    """main.py:42-102 without the GUI: depth cut, track, integrate every `integrate_interval` frames."""
+    depth = torch.where((depth < depth_cut[0]) | (depth > depth_cut[1]), torch.full_like(depth, float("nan")), depth)
+    pose = trk.track_camera(rgb, depth, calib, first_iso if len(trk.all_pd_pose) == 0 else None)
+    pc, nrm = trk.last_processed_pc
+    if frame_id % integrate_interval == 0:
+        m.integrate_keyframe(pose @ pc, pose.rotation @ nrm, do_optimize=False)
+    return pose
+
+
+def run_ours(args):
+    dfb = importlib.import_module("nerf-fusion_b200")
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    K, Wm = args.steps, args.warmup
+    n_frames = K + Wm
+    calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
+    first_iso = dfb.Isometry(q=dfb.Quaternion(array=dfb.synth.FIRST_TQ[3:]), t=np.array(dfb.synth.FIRST_TQ[:3]))
+    frames, seq = gen_frames(dfb, n_frames, dev, seed=rank)          # synthetic input, generated on the device, untimed
+    host_frames = [(d.cpu().pin_memory(), c.cpu().pin_memory()) for d, c in frames]
+    h2d = frames[0][0].numel() * 4 + frames[0][1].numel() * 4
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(e2e):
+        m, trk = make_system(dfb, dev)
+        hg_events = []
+        orig = trk.compute_sdf_Hg
+
+        def timed_sdf(n_iter, last_pose, cur_delta_pose, obs_xyz, no_grad=False):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orig(n_iter, last_pose, cur_delta_pose, obs_xyz, no_grad)
+            b.record()
+            hg_events.append((a, b, float(trk._hg_host[43]), not no_grad))
+            return out
+        poses = []
+        for i in range(Wm):
+            d, c = (t.to(dev, non_blocking=True) for t in host_frames[i]) if e2e else frames[i]
+            poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))
+        trk.compute_sdf_Hg = timed_sdf
+        dfb._lib.CALLS.clear()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        t0.record()
+        with ClockSampler(local) as cs:
+            for i in range(Wm, n_frames):
+                l2_flush.zero_()                                                  # cold L2 for every frame
+                if e2e:
+                    d, c = (t.to(dev, non_blocking=True) for t in host_frames[i])
+                else:
+                    d, c = frames[i]
+                poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))      # pose read back = D2H of H,g,e per GN term
+            t1.record()
+            barrier()
+        wall = time.perf_counter() - wall0
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = dfb._lib.kernel_launches()
+        # dominant kernel: the fused SDF Gauss-Newton term
+        dur, flops, n_launch = 0.0, 0.0, 0
+        for a, b, cnt, with_J in hg_events:
+            dur += a.elapsed_time(b) * 1e-3
+            flops += cnt * (FLOP_FWD_BWD if with_J else FLOP_FWD)
+            n_launch += 1
+        err_t = max(float(np.abs(p.t - seq.poses[i][1]).max()) for i, p in enumerate(poses))
+        return dict(ms=ms, wall=wall, launches=launches, hg_time=dur, hg_flops=flops, hg_launches=n_launch, clocks=cs.summary(),
+                    n_occupied=m.n_occupied, sdf_evals=trk.n_sdf_evals, rgb_evals=trk.n_rgb_evals, track_err=err_t,
+                    n_points=int(trk.last_processed_pc[0].size(0)))
+
+    res = run(e2e=False)
+    res_e2e = run(e2e=True)
+    if rank != 0:
+        return
+    pk = peaks()
+    value = world * K / (res["ms"] * 1e-3)
+    e2e_value = world * K / (res_e2e["ms"] * 1e-3)
+    ach = res["hg_flops"] / max(res["hg_time"], 1e-12) / 1e12
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(res["ms"] / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_rank": K, "points_per_frame": res["n_points"], "voxels": res["n_occupied"],
+                   "sdf_gn_evals_per_frame": round(res["sdf_evals"] / n_frames, 1), "rgb_gn_evals_per_frame": round(res["rgb_evals"] / n_frames, 1),
+                   "l2": "flushed before every frame (192 MiB write)", "parallelism": "replicas" if world > 1 else "single",
+                   "max_track_err_m": round(res["track_err"], 5), "timed_by": "cuda events around the K-frame loop, max over ranks",
+                   "wall_s": round(res["wall"], 3)},
+        "clocks": res["clocks"],
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(640 * (res_e2e["sdf_evals"] + res_e2e["rgb_evals"]) / n_frames)},
+        "gpu_launches": int(res["launches"]),
+        "roofline": {"bound": "tensor", "kernel": "sdf_hg_kernel (fused decoder fwd+bwd+JtJ, FP32 CUDA-core engine this round)",
+                     "achieved": round(ach, 3), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / pk["bf16_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                     "launches": res["hg_launches"], "avg_launch_us": round(1e6 * res["hg_time"] / max(res["hg_launches"], 1), 1)},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_reference(sample_frames=1, quiet=True)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference(sample_frames=1, quiet=False):
+    """The reference algorithm on the host cores (oracle port, torch CPU, all threads).  Bounded sample: ONE keyframe
+    cycle of the workload -- preprocess one 640x480 frame, integrate it, then time ONE Gauss-Newton evaluation of
+    each kind the config uses (sdf with Jacobian, rgb at levels 2/1/0) and compose a frame from the configured
+    iteration counts (10 x rgb2, 10 x (sdf+rgb1), 50 x (sdf+rgb0), + 3 evaluation-only passes)."""
+    from oracle import tracker_oracle as TO, nets
+    from util import make_oracle_map, GOLD
+    dfb = importlib.import_module("nerf-fusion_b200")
+    torch.set_num_threads(os.cpu_count() or 1)
+    W = nets.load_weights(GOLD / "weights.npz")
+    seq = dfb.synth.SyntheticSequence(n_frames=2)
+    (d0, c0), (d1, c1) = seq.frame(0), seq.frame(1)
+    for d in (d0, d1):
+        d[(d < 0.5) | (d > 5.0)] = float("nan")
+    t = time.perf_counter(); P, N = TO.preprocess(d1.numpy(), dfb.synth.ICL_CALIB); t_pre = time.perf_counter() - t
+    om = make_oracle_map(W)
+    last = TO.Pose(TO.Quaternion(array=dfb.synth.FIRST_TQ[3:]), np.array(dfb.synth.FIRST_TQ[:3]))
+    Pt = torch.from_numpy(P)
+    t = time.perf_counter(); om.integrate_keyframe(last.apply(Pt), torch.from_numpy(N) @ torch.from_numpy(last.R).float().T); t_int = time.perf_counter() - t
+    delta = TO.Pose.from_twist(np.array([0.002, -0.001, 0.002, 0.001, -0.001, 0.0005]))
+    TO.compute_sdf_Hg(om, last, delta, Pt)
+    t = time.perf_counter(); TO.compute_sdf_Hg(om, last, delta, Pt); t_sdf = time.perf_counter() - t
+    I0, D0, _ = TO.image_pyramid(c0.mean(-1), d0); I1, D1, G1 = TO.image_pyramid(c1.mean(-1), d1)
+    t_rgb = []
+    for lvl in (0, 1, 2):
+        t = time.perf_counter(); TO.compute_rgb_Hg((I0, D0), lvl, delta, I1, D1, G1, dfb.synth.ICL_CALIB); t_rgb.append(time.perf_counter() - t)
+    frame_s = t_pre + t_int / 20.0 + 11 * t_rgb[2] + 11 * (t_sdf + t_rgb[1]) + 51 * (t_sdf + t_rgb[0])
+    return {"value": round(1.0 / frame_s, 5), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 frame: preprocess {t_pre:.2f}s, integrate {t_int:.2f}s/20, sdf eval {t_sdf:.3f}s ({P.shape[0]} pts), "
+                      f"rgb evals {t_rgb[0]:.3f}/{t_rgb[1]:.3f}/{t_rgb[2]:.3f}s (levels 0/1/2); frame = configured iteration counts"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    t0 = time.perf_counter()
+    vals = []
+    steps = max(1, min(args.steps, 2)); warm = min(args.warmup, 1)
+    for i in range(warm + steps):
+        r = cpu_reference()
+        if i >= warm:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": steps, "warmup": warm, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": dict(vals[-1], value=round(v, 5)),
+            "e2e": {"value": round(v, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": round(time.perf_counter() - t0, 1)}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -84,7 +84,8 @@ int dfb_point_box_filter(const float* points, const float* normals, int n, float
                          void* stream);
 
 /* system.ext.groupby_sum (indexing.cpp:3-4, indexing.cu:59-71,89-109): sum (C,L) f32 and count (C,) i32 of
- * values (n,L) grouped by indices (n,) i64.  Outputs are zeroed here. */
+ * values (n,L) grouped by indices (n,) i64.  Outputs are zeroed here.  Like the reference kernel, `count` is
+ * incremented once per element, i.e. it holds L x (number of rows in the group). */
 int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, int C, float* sum, int32_t* count,
                     void* stream);
 

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) groupby_sum_kernel(const float* __restric
   long long g = indices[i];
   if (g < 0 || g >= C) return;
   atomicAdd(&sum[g * L + l], values[t]);
-  if (l == 0) atomicAdd(&count[g], 1);
+  if (l == 0) atomicAdd(&count[g], L);   // the reference bumps the count once per ELEMENT (indexing.cu:69-70), i.e. L per row
 }
 
 }  // namespace dfb
@@ -469,8 +469,9 @@ extern "C" {
 
 int dfb_unproject_depth(const float* depth, int H, int W, float fx, float fy, float cx, float cy, float* pc,
                         void* stream) {
-  DFB_CHECK_ARG(depth && pc && H >= 0 && W >= 0, "unproject_depth");
+  DFB_CHECK_ARG(H >= 0 && W >= 0, "unproject_depth");
   if (H * W == 0) return DFB_OK;
+  DFB_CHECK_ARG(depth && pc, "unproject_depth: null pointer");
   unproject_kernel<<<div_up((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(depth, H, W, fx, fy, cx, cy, pc);
   DFB_LAUNCH_CHECK();
   return DFB_OK;

@@ -221,12 +221,14 @@ def estimate_normals(points, max_nn, radius, cam_xyz):
 # indexing / torch_scatter
 # ----------------------------------------------------------------------------------------------
 def groupby_sum(values, indices, C):
-    """indexing.cu:59-71,89-109: per-group sum (fp32) and int32 count.  Sequential order here; the
-    reference's atomics are order-nondeterministic, so callers compare with a tolerance."""
+    """indexing.cu:59-71,89-109: per-group sum (fp32) and int32 "count".  Sequential order here; the
+    reference's atomics are order-nondeterministic, so callers compare with a tolerance.  Note the reference
+    increments the count from every one of the L threads of a row's block (indexing.cu:69-70), so its count is
+    L x (rows in the group) -- confirmed against the reference's own kernel on a B200 (tests/test_gpu_refext.py)."""
     values = np.asarray(values, dtype=f32); indices = np.asarray(indices, dtype=np.int64)
     s = np.zeros((int(C), values.shape[1]), dtype=f32)
     np.add.at(s, indices, values)
-    c = np.bincount(indices, minlength=int(C)).astype(np.int32)
+    c = (np.bincount(indices, minlength=int(C)) * values.shape[1]).astype(np.int32)
     return s, c
 
 

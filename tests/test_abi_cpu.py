@@ -36,6 +36,7 @@ def test_host_only_entry_points():
     assert lib.dfb_decode_cubes_ws_bytes(1000, 4) >= 1000 * 64 * 8
     # argument validation happens before any CUDA call
     assert lib.dfb_unproject_depth(None, 4, 4, 1.0, 1.0, 0.0, 0.0, None, None) == -1
+    assert lib.dfb_unproject_depth(None, 0, 4, 1.0, 1.0, 0.0, 0.0, None, None) == 0          # empty input is a no-op
     assert b"unproject" in lib.dfb_last_error()
 
 

@@ -66,3 +66,17 @@ def sort_rows(a):
     a = np.asarray(a)
     idx = np.lexsort(a.reshape(a.shape[0], -1).T[::-1])
     return a[idx], idx
+
+
+def match_rows(a, b, tol):
+    """Order-free comparison of two row sets: every row of `a` has a distinct partner in `b` within `tol` (max-abs).
+    Returns (perm, max_err) with a[i] ~ b[perm[i]]."""
+    from scipy.spatial import cKDTree
+    a = np.asarray(a, dtype=np.float64).reshape(len(a), -1); b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if len(a) == 0:
+        return np.zeros(0, dtype=np.int64), 0.0
+    d, j = cKDTree(b).query(a, k=1, p=np.inf)
+    assert d.max() < tol, f"unmatched row: max distance {d.max()}"
+    assert len(np.unique(j)) == len(j) or np.unique(np.round(a, 5), axis=0).shape[0] < len(a), "matching is not one-to-one"
+    return j, float(d.max())

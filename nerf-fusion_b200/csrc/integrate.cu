@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) ik_mask_mark_kernel(MapI M, int n, const 
   const bool keep = g >= 0 && (M.prune_min <= 0 || grid_count[g] > M.prune_min);
   mask[i] = keep ? 1 : 0;
   if (!keep || indexer[g] != -1) return;
-  const uint32_t old = atomicOr(&bits[g >> 5], 1u << (g & 31));
-  if (old & (1u << (g & 31))) return;          // another point of this voxel already handled the neighbours
+  // (the bit of g may already have been set by a NEIGHBOUR's dilation, so it says nothing about g's own neighbours:
+  //  every kept point marks all seven cells; the plain read filters most of the redundant atomics)
+  if (!(bits[g >> 5] & (1u << (g & 31)))) atomicOr(&bits[g >> 5], 1u << (g & 31));
   const int x = g / (M.ny * M.nz), y = (g / M.nz) % M.ny, z = g % M.nz;
   const int nb[6] = {lin_id(M, max(x - 1, 0), y, z), lin_id(M, min(x + 1, M.nx - 1), y, z),
                      lin_id(M, x, max(y - 1, 0), z), lin_id(M, x, min(y + 1, M.ny - 1), z),

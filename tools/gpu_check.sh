@@ -19,7 +19,7 @@ fi
 if [[ "$what" == *ncu* ]]; then
   CMD="python bench.py --steps 2 --warmup 3"
   timeout 600 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base mangled -k regex:3dfb -s 1500 -c 1500 \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base mangled -k regex:3dfb -s ${NCU_SKIP:-300} -c ${NCU_COUNT:-1200} \
       --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-sdf_hg_kernel} -s 30 -c 2 \

@@ -3,43 +3,12 @@
 // (compute_sdf_Hg), network/di_decoder.py:55-86, network/utility.py:61-126,129-149.
 #include <algorithm>
 
+#include <cstdlib>
+
+#include "decoder_common.cuh"
 #include "decoder_simt.cuh"
 
 namespace dfb {
-
-struct MapDev {
-  int nx, ny, nz;
-  float bx, by, bz, vs, inv_vs;
-  int div_mode;
-  float ignore_th;
-};
-
-static MapDev to_dev(const dfb_map_params* p) {
-  MapDev m;
-  m.nx = p->nx; m.ny = p->ny; m.nz = p->nz;
-  m.bx = p->bound_min[0]; m.by = p->bound_min[1]; m.bz = p->bound_min[2];
-  m.vs = p->voxel_size; m.inv_vs = 1.0f / p->voxel_size;
-  m.div_mode = p->div_mode; m.ignore_th = p->ignore_count_th;
-  return m;
-}
-
-// map.py:566-576.  The reference does not bounds-check (map.py:313); out-of-grid points are reported invalid here.
-__device__ __forceinline__ bool map_lookup(const MapDev& M, float px, float py, float pz, const int64_t* __restrict__ indexer,
-                                           const float* __restrict__ obs_count, long long& slot, float rel[3]) {
-  const float xn = div_vs(__fsub_rn(px, M.bx), M.vs, M.inv_vs, M.div_mode);
-  const float yn = div_vs(__fsub_rn(py, M.by), M.vs, M.inv_vs, M.div_mode);
-  const float zn = div_vs(__fsub_rn(pz, M.bz), M.vs, M.inv_vs, M.div_mode);
-  const float cx = ceilf(xn) - 1.0f, cy = ceilf(yn) - 1.0f, cz = ceilf(zn) - 1.0f;   // exact in fp32 for grid-sized values
-  if (!(cx >= 0.f && cx < (float)M.nx && cy >= 0.f && cy < (float)M.ny && cz >= 0.f && cz < (float)M.nz)) return false;
-  const long long lin = (long long)cz + (long long)M.nz * (long long)cy + (long long)M.nz * M.ny * (long long)cx;
-  slot = indexer[lin];
-  if (slot < 0) return false;
-  if (!(obs_count[slot] > M.ignore_th)) return false;
-  rel[0] = __fsub_rn(__fsub_rn(xn, cx), 0.5f);
-  rel[1] = __fsub_rn(__fsub_rn(yn, cy), 0.5f);
-  rel[2] = __fsub_rn(__fsub_rn(zn, cz), 0.5f);
-  return true;
-}
 
 __device__ __forceinline__ void load_query(DecSmem& S, const float* __restrict__ latent_row, const float rel[3], bool valid) {
   const int tid = threadIdx.x;
@@ -104,7 +73,7 @@ __global__ void __launch_bounds__(DEC_T, 1) get_sdf_kernel(MapDev M, const float
       if (valid) {
         gs = g_sdf ? g_sdf[i] * (1.0f - s * s) : 0.f;
         // d softplus(u)/du = sigmoid(u) (1 past the threshold)
-        const float dsp = u > 20.f ? 1.0f : 1.0f / (1.0f + expf(-u));
+        const float dsp = softplus_grad(u);
         gu = g_std ? g_std[i] * 0.5f * dsp : 0.f;
       }
       float g[3];
@@ -120,18 +89,6 @@ __global__ void __launch_bounds__(DEC_T, 1) get_sdf_kernel(MapDev M, const float
 // ------------------------------------------------------------------------------------------------
 // compute_sdf_Hg fused
 // ------------------------------------------------------------------------------------------------
-struct PoseDev {
-  float Rt[9], tt[3];   // total = last o delta
-  float Rd[9], td[3];   // delta
-  float Rl[9];          // last
-};
-
-__device__ __forceinline__ void xform(const float* R, const float* t, float x, float y, float z, float o[3]) {
-  // other @ R^T + t  (motion_util.py:323-328)
-#pragma unroll
-  for (int j = 0; j < 3; ++j) o[j] = fmaf(z, R[3 * j + 2], fmaf(y, R[3 * j + 1], x * R[3 * j])) + t[j];
-}
-
 __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
                                                           const int64_t* __restrict__ indexer, const float* __restrict__ latents,
                                                           const float* __restrict__ obs_count, const float* __restrict__ blob,
@@ -167,14 +124,7 @@ __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
         float gw[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) gw[a] = div_vs(g[a], M.vs, M.inv_vs, M.div_mode);
-        // Lai = grad @ R_last^T  (tracker.py:202-203): Lai_j = sum_k grad_k * R_last[j][k]
-#pragma unroll
-        for (int j = 0; j < 3; ++j) J[j] = fmaf(gw[2], P.Rl[3 * j + 2], fmaf(gw[1], P.Rl[3 * j + 1], gw[0] * P.Rl[3 * j]));
-        float d[3];
-        xform(P.Rd, P.td, pc[0], pc[1], pc[2], d);            // cur_dxyz (tracker.py:201)
-        J[3] = d[1] * J[2] - d[2] * J[1];                     // cross(cur_dxyz, Lai) (tracker.py:204)
-        J[4] = d[2] * J[0] - d[0] * J[2];
-        J[5] = d[0] * J[1] - d[1] * J[0];
+        sdf_jacobian(P, gw, pc, J);
       }
     }
     if (valid) hg_accumulate(acc, J, r, robust_w(r, robust, robust_k), with_J != 0);
@@ -185,12 +135,6 @@ __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
 // ------------------------------------------------------------------------------------------------
 // decode_cubes
 // ------------------------------------------------------------------------------------------------
-// lattice coordinate of utility.get_samples minus the 0.5 network offset, fp32 op order of
-// `(idx * vsize + a) - 0.5` (utility.py:143-147, map.py:646-647)
-__device__ __forceinline__ float lattice(int i, float vsize, float a) {
-  return __fsub_rn(__fadd_rn(__fmul_rn((float)i, vsize), a), 0.5f);
-}
-
 // low-resolution pass: query id = b * r^3 + cell
 __global__ void __launch_bounds__(DEC_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ,
                                                             int B, int r, float vsize, float a, const float* __restrict__ blob,

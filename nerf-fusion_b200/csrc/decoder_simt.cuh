@@ -5,7 +5,7 @@
 // weights staged through shared memory in 64-output chunks read as warp-uniform broadcasts.
 // Math restated from network/di_decoder.py:55-86; the reverse pass is SURVEY.md Appendix B.
 #pragma once
-#include "common.cuh"
+#include "decoder_common.cuh"
 
 namespace dfb {
 
@@ -104,10 +104,6 @@ __device__ __forceinline__ void dense(DecSmem& S, const float* __restrict__ in1,
     }
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ float softplus_torch(float u) {   // F.softplus, beta 1, threshold 20
-  return u > 20.f ? u : log1pf(expf(u));
 }
 
 // Forward for the tile; x0 must already hold the 32 inputs of this thread's query.  Returns z (pre-tanh) and u

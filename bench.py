@@ -203,7 +203,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(640 * (res_e2e["sdf_evals"] + res_e2e["rgb_evals"]) / n_frames)},
         "gpu_launches": int(res["launches"]),
-        "roofline": {"bound": "tensor", "kernel": "sdf_hg_kernel (fused decoder fwd+bwd+JtJ, FP32 CUDA-core engine this round)",
+        "roofline": {"bound": "tensor", "kernel": "sdf_hg_kernel (tcgen05 FP16 engine: fused decoder fwd+bwd+JtJ reduction)",
                      "achieved": round(ach, 3), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["bf16_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
                      "launches": res["hg_launches"], "avg_launch_us": round(1e6 * res["hg_time"] / max(res["hg_launches"], 1), 1)},

@@ -49,6 +49,11 @@ int dfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * ---------------------------------------------------------------------------------------------- */
 size_t dfb_decoder_blob_floats(void);
 size_t dfb_encoder_blob_floats(void);
+/* Decoder engine used by dfb_decoder_forward / dfb_get_sdf / dfb_sdf_hg / dfb_decode_cubes:
+ * 1 = tcgen05 (FP16 operands, FP32 accumulation in TMEM; default), 0 = FP32 CUDA cores (exact-precision path).
+ * Also settable with the environment variable DFB_DECODER_ENGINE before the first call. */
+int dfb_set_decoder_engine(int engine);
+int dfb_get_decoder_engine(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- image / point-cloud preprocessing

@@ -251,14 +251,29 @@ static int dec_grid(long long n) { return (int)std::min<long long>(div_up(n, DEC
 
 using namespace dfb;
 
+// engine selection: 1 = tcgen05 FP16 (default), 0 = FP32 CUDA cores.  Env DFB_DECODER_ENGINE or dfb_set_decoder_engine().
+static int g_engine = -1;
+int dfb::decoder_engine() {
+  if (g_engine < 0) {
+    const char* e = getenv("DFB_DECODER_ENGINE");
+    g_engine = e ? atoi(e) : 1;
+  }
+  return g_engine;
+}
+constexpr int TC_BLOB_BYTES = 122880 + 6144;   // decoder_tc.cu: tc::BLOB_BYTES
+static inline const void* tc_part(const float* blob) { return blob + DB_TOTAL; }
+
 extern "C" {
 
-size_t dfb_decoder_blob_floats(void) { return DB_TOTAL; }
+size_t dfb_decoder_blob_floats(void) { return DB_TOTAL + TC_BLOB_BYTES / 4; }
+int dfb_set_decoder_engine(int engine) { g_engine = engine ? 1 : 0; return DFB_OK; }
+int dfb_get_decoder_engine(void) { return decoder_engine(); }
 
 int dfb_decoder_forward(const float* x, int n, const float* decoder_blob, float* sdf, float* std_, void* stream) {
   DFB_CHECK_ARG(n >= 0, "decoder_forward");
   if (n == 0) return DFB_OK;
   DFB_CHECK_ARG(x && decoder_blob && sdf && std_, "decoder_forward: null pointer");
+  if (decoder_engine() == 1) return tc_decoder_explicit(x, n, tc_part(decoder_blob), sdf, std_, (cudaStream_t)stream);
   int rc = set_dec_smem(decoder_explicit_kernel);
   if (rc) return rc;
   decoder_explicit_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), (cudaStream_t)stream>>>(x, n, decoder_blob, sdf, std_);
@@ -272,6 +287,9 @@ int dfb_get_sdf(const dfb_map_params* h_params, const float* xyz, int n, const i
   DFB_CHECK_ARG(h_params && n >= 0, "get_sdf");
   if (n == 0) return DFB_OK;
   DFB_CHECK_ARG(xyz && indexer && latent_vecs && voxel_obs_count && decoder_blob && valid, "get_sdf: null pointer");
+  if (decoder_engine() == 1)
+    return tc_get_sdf(to_dev(h_params), xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), sdf, std_, valid, g_sdf,
+                      g_std, grad_xyz, (cudaStream_t)stream);
   int rc = set_dec_smem(get_sdf_kernel);
   if (rc) return rc;
   get_sdf_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), (cudaStream_t)stream>>>(to_dev(h_params), xyz, n, indexer, latent_vecs,
@@ -290,9 +308,15 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
   DFB_CUDA(cudaMemsetAsync(out44, 0, sizeof(double) * 80, s));
   if (n == 0) return DFB_OK;
   DFB_CHECK_ARG(obs_xyz && indexer && latent_vecs && voxel_obs_count && decoder_blob, "sdf_hg: null pointer");
-  PoseDev P;
-  for (int i = 0; i < 9; ++i) { P.Rt[i] = h_pose[i]; P.Rd[i] = h_pose[12 + i]; P.Rl[i] = h_pose[24 + i]; }
-  for (int i = 0; i < 3; ++i) { P.tt[i] = h_pose[9 + i]; P.td[i] = h_pose[21 + i]; }
+  const PoseDev P = to_pose(h_pose);
+  if (decoder_engine() == 1) {
+    int rc = tc_sdf_hg(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), robust, robust_k,
+                       compute_J, packed, s);
+    if (rc) return rc;
+    launch_hg_expand(packed, out44, s);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  }
   int rc = set_dec_smem(sdf_hg_kernel);
   if (rc) return rc;
   sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count,
@@ -329,11 +353,19 @@ int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r,
   const float a32 = (float)sa;
   const float v_low = (float)((sb - sa) / (r - 1));
   const float v_high = (float)((sb - sa) / (2 * r - 1));
+  DFB_CUDA(cudaMemsetAsync(refine_count, 0, sizeof(int) * 4, s));
+  const long long nh_tc = (long long)B * r3 * 8;
+  if (decoder_engine() == 1) {
+    int rc = tc_cube_low(latent_vecs, occ, B, r, v_low, a32, tc_part(decoder_blob), low_sdf, low_std, s);
+    if (rc) return rc;
+    cube_upsample_kernel<<<div_up(nh_tc, 256), 256, 0, s>>>(low_sdf, low_std, B, r, refine_band, cube_sdf, cube_std, refine_count, refine_list);
+    DFB_LAUNCH_CHECK();
+    return tc_cube_refine(latent_vecs, occ, r, v_high, a32, tc_part(decoder_blob), refine_count, refine_list, cube_sdf, cube_std, s);
+  }
   int rc = set_dec_smem(cube_low_kernel);
   if (rc) return rc;
   rc = set_dec_smem(cube_refine_kernel);
   if (rc) return rc;
-  DFB_CUDA(cudaMemsetAsync(refine_count, 0, sizeof(int) * 4, s));
   cube_low_kernel<<<dec_grid((long long)B * r3), DEC_T, sizeof(DecSmem), s>>>(latent_vecs, occ, B, r, v_low, a32, decoder_blob, low_sdf, low_std);
   const long long nh = (long long)B * r3 * 8;
   cube_upsample_kernel<<<div_up(nh, 256), 256, 0, s>>>(low_sdf, low_std, B, r, refine_band, cube_sdf, cube_std, refine_count, refine_list);

@@ -1,0 +1,569 @@
+// tcgen05 decoder engine (sm_100a): the 5-layer decoder MLP, its reverse pass and the tracker reduction with the
+// weights RESIDENT in shared memory (one bulk-TMA load per CTA), activations as FP16 K-major SWIZZLE_128B tiles,
+// FP32 accumulators in TMEM, one elected thread issuing tcgen05.mma, 128 threads (one per query row = one TMEM lane)
+// running the epilogues (bias/ReLU/mask -> FP16 -> swizzled smem) between layers.
+//
+//   forward   D[128 x N] = A[128 x K] * W^T      A: activations (K-major), B: weight image (K-major)
+//   reverse   D[128 x K] = delta[128 x N] * W    A: deltas (K-major),      B: the SAME weight image read MN-major
+//
+// so one FP16 image per layer serves both passes (120 KB for the whole network).  Inputs are split hi+lo into the
+// two halves of the 64-wide input block (weights duplicated) so positions/latents enter with ~22 significant bits.
+// Math: network/di_decoder.py:55-86; reverse pass: SURVEY.md Appendix B.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "decoder_common.cuh"
+#include "decoder_simt.cuh"   // DS_* offsets of the FP32 "small" block (biases, heads, xyz taps)
+
+namespace dfb {
+namespace tc {
+
+constexpr int T = 128;          // query rows per tile = threads per tile group
+constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 warps, smem tiles, TMEM columns, barrier)
+constexpr int CTA_T = T * GROUPS;
+// ---- blob (bytes): FP16 swizzled images + FP32 small block; packed by weights.pack_decoder_tc -------------------
+constexpr int IMG_W0 = 0;          // [128 rows x 64]: cols 0..31 = W0, cols 32..63 = W0 again (lo halves of the input)
+constexpr int IMG_W1 = 16384;      // 2 blocks x [128 x 64]
+constexpr int IMG_W2 = 49152;      // 2 blocks x [ 96 x 64]
+constexpr int IMG_W3A = 73728;     // 2 blocks x [128 x 64]: W3[:, 0:96], cols 96..127 zero
+constexpr int IMG_W3B = 106496;    // [128 x 64]: W3[:, 96:128] twice (hi, lo)
+constexpr int IMG_END = 122880;
+constexpr int SMALL_BYTES = 6144;
+constexpr int BLOB_BYTES = IMG_END + SMALL_BYTES;
+// ---- shared memory (bytes from the 1024-aligned base) ------------------------------------------------------------
+constexpr int SM_SMALL = IMG_END;
+constexpr int SM_A = SM_SMALL + SMALL_BYTES;   // 129024 = 126 * 1024: activation tile, 2 blocks x [128 x 64] fp16
+constexpr int SM_XOFF = 32768;                 // input tile [128 x 64] fp16 (hi | lo), after the activation tile
+constexpr int SM_TILE_BYTES = 32768 + 16384;   // per tile group
+constexpr int SM_BAR = SM_A + GROUPS * SM_TILE_BYTES;   // mbarriers + TMEM slot
+constexpr int SM_TOTAL = SM_BAR + 64;
+constexpr int SM_ALLOC = SM_TOTAL + 1024;      // slack for manual 1024-byte alignment
+constexpr int TMEM_COLS = 128 * GROUPS;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a malformed descriptor must end in a trap (sticky launch error), never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int it = 0; it < (1 << 24); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+  return d;
+}
+// 32-bit instruction descriptor, kind::f16: F16 x F16 -> F32, A K-major, M = 128 (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t instr_desc(int N, bool b_mn_major) {
+  return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
+}
+
+struct Ctx {
+  uint8_t* sm;        // 1024-aligned base (generic)
+  uint32_t sa;        // same, shared-window address
+  uint32_t tmem;      // TMEM address of this group's accumulator (lane 0)
+  uint32_t tmem_base; // allocation base
+  int row, grp;       // row within the tile (= thread within the group), tile group
+  uint32_t a_off, x_off;   // byte offsets of this group's activation / input tiles
+  uint32_t mma_bar;   // shared address of the "MMA done" barrier
+  uint32_t phase;     // its parity
+  uint32_t mask[4][4];
+};
+
+// Thread 0 only.  K-major A (activation tile at a_addr, blocks of 16 KB), B = weight image at b_addr with b_rows rows per
+// 64-column block.  fwd: B read K-major; bwd: the same image read MN-major (k-step s = image rows 16s..16s+15).
+__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr, int b_rows, int ksteps, int N, bool bwd,
+                                      bool accumulate_first) {
+  const uint32_t idesc = instr_desc(N, bwd);
+  for (int s = 0; s < ksteps; ++s) {
+    const uint64_t ad = smem_desc(a_addr + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
+    const uint64_t bd = bwd ? smem_desc(b_addr + s * 2048, (uint32_t)b_rows * 128u, 1024)
+                            : smem_desc(b_addr + (s >> 2) * (b_rows * 128) + (s & 3) * 32, 16, 1024);
+    mma_f16(c.tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(T) : "memory"); }
+
+// all threads of the group: make the tile writes visible to the tensor core, then thread 0 issues; everyone waits for completion
+#define TC_LAYER(ISSUE_STMTS)                         \
+  do {                                                \
+    fence_proxy_async();                              \
+    tc_fence_before();                                \
+    group_sync(c.grp);                                \
+    if (c.row == 0) {                                 \
+      tc_fence_after();                               \
+      ISSUE_STMTS;                                    \
+      mma_commit(c.mma_bar);                          \
+    }                                                 \
+    mbar_wait(c.mma_bar, c.phase);                    \
+    c.phase ^= 1u;                                    \
+    tc_fence_after();                                 \
+  } while (0)
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// store 32 consecutive columns [col0, col0+32) of this thread's row into a swizzled K-major tile
+__device__ __forceinline__ void store_cols32(uint8_t* tile, int row, int col0, const float* h) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = (col0 >> 3) + q;   // 16-byte chunk index along K
+    uint4 v;
+    v.x = pack_h2(h[8 * q + 0], h[8 * q + 1]); v.y = pack_h2(h[8 * q + 2], h[8 * q + 3]);
+    v.z = pack_h2(h[8 * q + 4], h[8 * q + 5]); v.w = pack_h2(h[8 * q + 6], h[8 * q + 7]);
+    *reinterpret_cast<uint4*>(tile + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+  }
+}
+
+// hidden-layer forward epilogue: a = D + b, record [a > 0], write relu(a) as FP16 into the activation tile
+template <int NCOLS>
+__device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
+  const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  const int row = c.row;
+  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+#pragma unroll
+  for (int j = 0; j < NCOLS / 32; ++j) {
+    float v[32];
+    tmem_ld32(tbase + j * 32, v);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float a = v[i] + sm[bias_off + 32 * j + i];
+      m |= (a > 0.f ? 1u : 0u) << i;
+      v[i] = fmaxf(a, 0.f);
+    }
+    c.mask[layer][j] = m;
+    store_cols32(c.sm + c.a_off, row, 32 * j, v);
+  }
+}
+
+// reverse epilogue: delta = D * mask[layer] -> FP16 tile
+template <int NCOLS>
+__device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
+  const int row = c.row;
+  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+#pragma unroll
+  for (int j = 0; j < NCOLS / 32; ++j) {
+    float v[32];
+    tmem_ld32(tbase + j * 32, v);
+    const uint32_t m = c.mask[layer][j];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+    store_cols32(c.sm + c.a_off, row, 32 * j, v);
+  }
+}
+
+// write this thread's query (29 latent + 3 rel) as hi|lo FP16 halves into the input tile
+__device__ __forceinline__ void store_input(Ctx& c, const float* x32) {
+  float hi[32], lo[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float h = __half2float(__float2half_rn(x32[k]));
+    hi[k] = h;
+    lo[k] = x32[k] - h;
+  }
+  store_cols32(c.sm + c.x_off, c.row, 0, hi);
+  store_cols32(c.sm + c.x_off, c.row, 32, lo);
+}
+
+// forward pass of the tile; returns pre-activation heads z (sdf) and u (std)
+__device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
+  const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  TC_LAYER(issue(c, c.sa + c.x_off, c.sa + IMG_W0, 128, 4, 128, false, false));
+  epi_fwd<128>(c, 0, DS_B0);
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W1, 128, 8, 128, false, false));
+  epi_fwd<128>(c, 1, DS_B1);
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W2, 96, 8, 96, false, false));
+  epi_fwd<96>(c, 2, DS_B2);
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W3A, 128, 8, 128, false, false);
+           issue(c, c.sa + c.x_off, c.sa + IMG_W3B, 128, 4, 128, false, true));
+  // heads in FP32 straight from the accumulator (h3 never leaves TMEM/registers)
+  const int row = c.row;
+  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+  float zz = sm[DS_B4], uu = sm[DS_B4 + 1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[32];
+    tmem_ld32(tbase + j * 32, v);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float a = v[i] + sm[DS_B3 + 32 * j + i];
+      m |= (a > 0.f ? 1u : 0u) << i;
+      const float h = fmaxf(a, 0.f);
+      zz = fmaf(sm[DS_W4 + 32 * j + i], h, zz);
+      uu = fmaf(sm[DS_WU + 32 * j + i], h, uu);
+    }
+    c.mask[3][j] = m;
+  }
+  z = zz; u = uu;
+}
+
+// reverse pass: seeds on z and u -> d/d(xyz) in network units
+__device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, float g[3]) {
+  const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  const int row = c.row;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d[32];
+    const uint32_t m = c.mask[3][j];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int o = 32 * j + i;
+      const float dv = ((m >> i) & 1u) ? fmaf(seed_z, sm[DS_W4 + o], seed_u * sm[DS_WU + o]) : 0.f;
+      d[i] = dv;
+      gx = fmaf(sm[DS_W3X + 3 * o + 0], dv, gx);
+      gy = fmaf(sm[DS_W3X + 3 * o + 1], dv, gy);
+      gz = fmaf(sm[DS_W3X + 3 * o + 2], dv, gz);
+    }
+    store_cols32(c.sm + c.a_off, row, 32 * j, d);
+  }
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W3A, 128, 8, 128, true, false));   // delta2 = delta3 * W3[:, :96] (cols 96.. are 0)
+  epi_bwd<96>(c, 2);
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W2, 96, 6, 128, true, false));     // delta1 = delta2 * W2
+  epi_bwd<128>(c, 1);
+  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W1, 128, 8, 128, true, false));    // delta0 = delta1 * W1 (masked below)
+  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[32];
+    tmem_ld32(tbase + j * 32, v);
+    const uint32_t m = c.mask[0][j];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int o = 32 * j + i;
+      const float dv = ((m >> i) & 1u) ? v[i] : 0.f;
+      gx = fmaf(sm[DS_W0X + 3 * o + 0], dv, gx);
+      gy = fmaf(sm[DS_W0X + 3 * o + 1], dv, gy);
+      gz = fmaf(sm[DS_W0X + 3 * o + 2], dv, gz);
+    }
+  }
+  g[0] = gx; g[1] = gy; g[2] = gz;
+}
+
+extern __shared__ unsigned char tc_smem_raw[];
+
+// CTA prologue: align, barriers, TMEM, one bulk load of the whole network
+__device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  c.sm = tc_smem_raw + pad;
+  c.sa = raw + pad;
+  c.phase = 0;
+  c.row = threadIdx.x % T;
+  c.grp = threadIdx.x / T;
+  c.a_off = SM_A + c.grp * SM_TILE_BYTES;
+  c.x_off = c.a_off + SM_XOFF;
+  const uint32_t wbar = c.sa + SM_BAR, slot = c.sa + SM_BAR + 48;
+  c.mma_bar = c.sa + SM_BAR + 8 + 8 * c.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(wbar, 1);
+    for (int g = 0; g < GROUPS; ++g) mbar_init(c.sa + SM_BAR + 8 + 8 * g, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_alloc(slot, TMEM_COLS);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(wbar, BLOB_BYTES);
+    const char* src = reinterpret_cast<const char*>(blob);
+    for (int off = 0; off < BLOB_BYTES; off += 16128) {   // 8 chunks of 16128 B (multiple of 16)
+      const int n = min(16128, BLOB_BYTES - off);
+      bulk_g2s(c.sa + off, src + off, (uint32_t)n, wbar);
+    }
+  }
+  // zero the activation / input tiles once (unused K columns must be finite)
+  for (int i = threadIdx.x; i < GROUPS * SM_TILE_BYTES / 16; i += CTA_T) reinterpret_cast<uint4*>(c.sm + SM_A)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
+  c.tmem = c.tmem_base + 128u * c.grp;
+  mbar_wait(wbar, 0);
+}
+
+__device__ __forceinline__ void epilogue_free(Ctx& c) {
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
+}
+
+__device__ __forceinline__ void load_x(float* x32, const float* __restrict__ latent_row, const float rel[3], bool valid) {
+#pragma unroll
+  for (int k = 0; k < DFB_LATENT_DIM; ++k) x32[k] = valid ? __ldg(latent_row + k) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) x32[DFB_LATENT_DIM + k] = valid ? rel[k] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restrict__ x, int n, const void* __restrict__ blob,
+                                                        float* __restrict__ sdf, float* __restrict__ std_) {
+  Ctx c;
+  prologue(c, blob);
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+    const int i = (int)(tile * T) + c.row;
+    float x32[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x32[k] = i < n ? x[(size_t)i * 32 + k] : 0.f;
+    store_input(c, x32);
+    float z, u;
+    forward(c, z, u);
+    if (i < n) { sdf[i] = tanhf(z); std_[i] = 0.05f + 0.5f * softplus_torch(u); }
+  }
+  epilogue_free(c);
+}
+
+__global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float* __restrict__ xyz, int n, const int64_t* __restrict__ indexer,
+                                                       const float* __restrict__ latents, const float* __restrict__ obs_count,
+                                                       const void* __restrict__ blob, float* __restrict__ sdf, float* __restrict__ std_,
+                                                       uint8_t* __restrict__ valid_out, const float* __restrict__ g_sdf,
+                                                       const float* __restrict__ g_std, float* __restrict__ grad_xyz) {
+  Ctx c;
+  prologue(c, blob);
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+    const int i = (int)(tile * T) + c.row;
+    bool valid = false;
+    long long slot = 0;
+    float rel[3] = {0.f, 0.f, 0.f};
+    if (i < n) valid = map_lookup(M, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], indexer, obs_count, slot, rel);
+    float x32[32];
+    load_x(x32, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
+    store_input(c, x32);
+    float z, u;
+    forward(c, z, u);
+    const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
+    if (i < n) {
+      valid_out[i] = valid ? 1 : 0;
+      if (sdf) sdf[i] = valid ? s : 0.f;
+      if (std_) std_[i] = valid ? sd : 0.f;
+    }
+    if (grad_xyz) {
+      float gs = 0.f, gu = 0.f;
+      if (valid) {
+        gs = g_sdf ? g_sdf[i] * (1.0f - s * s) : 0.f;
+        gu = g_std ? g_std[i] * 0.5f * softplus_grad(u) : 0.f;
+      }
+      float g[3];
+      backward(c, gs, gu, g);
+      if (i < n) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) grad_xyz[3 * (size_t)i + a] = valid ? div_vs(g[a], M.vs, M.inv_vs, M.div_mode) : 0.f;
+      }
+    }
+  }
+  epilogue_free(c);
+}
+
+__global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
+                                                      const int64_t* __restrict__ indexer, const float* __restrict__ latents,
+                                                      const float* __restrict__ obs_count, const void* __restrict__ blob, int robust,
+                                                      float robust_k, int with_J, double* __restrict__ packed) {
+  Ctx c;
+  prologue(c, blob);
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+    const int i = (int)(tile * T) + c.row;
+    bool valid = false;
+    long long slot = 0;
+    float rel[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
+    if (i < n) {
+      pc[0] = obs[3 * (size_t)i]; pc[1] = obs[3 * (size_t)i + 1]; pc[2] = obs[3 * (size_t)i + 2];
+      float pw[3];
+      xform(P.Rt, P.tt, pc[0], pc[1], pc[2], pw);
+      valid = map_lookup(M, pw[0], pw[1], pw[2], indexer, obs_count, slot, rel);
+    }
+    float x32[32];
+    load_x(x32, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
+    store_input(c, x32);
+    float z, u;
+    forward(c, z, u);
+    const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
+    const float r = s / sd;
+    float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (with_J) {
+      float g[3];
+      backward(c, valid ? (1.0f - s * s) / sd : 0.f, 0.f, g);
+      if (valid) {
+        float gw[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gw[a] = div_vs(g[a], M.vs, M.inv_vs, M.div_mode);
+        sdf_jacobian(P, gw, pc, J);
+      }
+    }
+    if (valid) hg_accumulate(acc, J, r, robust_w(r, robust, robust_k), with_J != 0);
+  }
+  epilogue_free(c);
+  block_reduce_atomic<29, CTA_T>(acc, packed);
+}
+
+__global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int B, int r,
+                                                        float vsize, float a, const void* __restrict__ blob, float* __restrict__ low_sdf,
+                                                        float* __restrict__ low_std) {
+  Ctx c;
+  prologue(c, blob);
+  const long long r3 = (long long)r * r * r, n = (long long)B * r3;
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+    const long long i = tile * T + c.row;
+    const bool valid = i < n;
+    float rel[3] = {0.f, 0.f, 0.f};
+    long long slot = 0;
+    if (valid) {
+      const int b = (int)(i / r3), cc = (int)(i - (long long)b * r3);
+      rel[0] = lattice(cc / (r * r), vsize, a); rel[1] = lattice((cc / r) % r, vsize, a); rel[2] = lattice(cc % r, vsize, a);
+      slot = occ[b];
+    }
+    float x32[32];
+    load_x(x32, latents + slot * DFB_LATENT_DIM, rel, valid);
+    store_input(c, x32);
+    float z, u;
+    forward(c, z, u);
+    if (valid) { low_sdf[i] = tanhf(z); low_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+  }
+  epilogue_free(c);
+}
+
+__global__ void __launch_bounds__(CTA_T, 1) cube_refine_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int r, float vsize,
+                                                           float a, const void* __restrict__ blob, const int* __restrict__ refine_count,
+                                                           const long long* __restrict__ refine_list, float* __restrict__ cube_sdf,
+                                                           float* __restrict__ cube_std) {
+  Ctx c;
+  prologue(c, blob);
+  const int R = 2 * r;
+  const long long R3 = (long long)R * R * R;
+  const int n = *refine_count;
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+    const int t = (int)(tile * T) + c.row;
+    const bool valid = t < n;
+    float rel[3] = {0.f, 0.f, 0.f};
+    long long slot = 0, i = 0;
+    if (valid) {
+      i = refine_list[t];
+      const int b = (int)(i / R3), cc = (int)(i - (long long)b * R3);
+      rel[0] = lattice(cc / (R * R), vsize, a); rel[1] = lattice((cc / R) % R, vsize, a); rel[2] = lattice(cc % R, vsize, a);
+      slot = occ[b];
+    }
+    float x32[32];
+    load_x(x32, latents + slot * DFB_LATENT_DIM, rel, valid);
+    store_input(c, x32);
+    float z, u;
+    forward(c, z, u);
+    if (valid) { cube_sdf[i] = -tanhf(z); cube_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+  }
+  epilogue_free(c);
+}
+
+template <typename K>
+static int prep(K kernel) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
+  return DFB_OK;
+}
+static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, CTA_T), (long long)sm_count()); }
+
+}  // namespace tc
+
+int tc_decoder_explicit(const float* x, int n, const void* blob, float* sdf, float* std_, cudaStream_t s) {
+  int rc = tc::prep(tc::explicit_kernel);
+  if (rc) return rc;
+  tc::explicit_kernel<<<tc::grid_for(n), tc::CTA_T, tc::SM_ALLOC, s>>>(x, n, blob, sdf, std_);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer, const float* latents, const float* obs_count,
+               const void* blob, float* sdf, float* std_, uint8_t* valid, const float* g_sdf, const float* g_std, float* grad_xyz,
+               cudaStream_t s) {
+  int rc = tc::prep(tc::get_sdf_kernel);
+  if (rc) return rc;
+  tc::get_sdf_kernel<<<tc::grid_for(n), tc::CTA_T, tc::SM_ALLOC, s>>>(M, xyz, n, indexer, latents, obs_count, blob, sdf, std_, valid, g_sdf,
+                                                                    g_std, grad_xyz);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const int64_t* indexer, const float* latents,
+              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s) {
+  int rc = tc::prep(tc::sdf_hg_kernel);
+  if (rc) return rc;
+  tc::sdf_hg_kernel<<<tc::grid_for(n), tc::CTA_T, tc::SM_ALLOC, s>>>(M, P, obs, n, indexer, latents, obs_count, blob, robust, robust_k, with_J,
+                                                                   packed);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int tc_cube_low(const float* latents, const int64_t* occ, int B, int r, float vsize, float a, const void* blob, float* low_sdf,
+                float* low_std, cudaStream_t s) {
+  int rc = tc::prep(tc::cube_low_kernel);
+  if (rc) return rc;
+  tc::cube_low_kernel<<<tc::grid_for((long long)B * r * r * r), tc::CTA_T, tc::SM_ALLOC, s>>>(latents, occ, B, r, vsize, a, blob, low_sdf, low_std);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int tc_cube_refine(const float* latents, const int64_t* occ, int r, float vsize, float a, const void* blob, const int* refine_count,
+                   const long long* refine_list, float* cube_sdf, float* cube_std, cudaStream_t s) {
+  int rc = tc::prep(tc::cube_refine_kernel);
+  if (rc) return rc;
+  tc::cube_refine_kernel<<<sm_count(), tc::CTA_T, tc::SM_ALLOC, s>>>(latents, occ, r, vsize, a, blob, refine_count, refine_list, cube_sdf, cube_std);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // namespace dfb

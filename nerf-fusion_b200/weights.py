@@ -66,7 +66,37 @@ def pack_decoder(W):
     small[1120:1120 + 384] = W0[:, 29:32].reshape(-1)
     small[1504] = M["b4"][0]; small[1505] = M["bu"][0]
     blob = np.concatenate(parts + [small]).astype(np.float32)
-    return blob
+    tc = pack_decoder_tc(M, small)
+    return np.concatenate([blob, tc.view(np.float32)])
+
+
+def _swizzled_image(mat):
+    """mat (rows, K) float -> FP16 K-major SWIZZLE_128B image: blocks of 64 columns, each [rows][128 B]; the 16-byte
+    chunk c of row r is stored at chunk position c ^ (r & 7) (csrc/decoder_tc.cu store_cols32 uses the same map)."""
+    rows, K = mat.shape
+    assert K % 64 == 0 and rows % 8 == 0
+    h = mat.astype(np.float16)
+    out = np.zeros((K // 64, rows, 8, 8), dtype=np.float16)
+    r = np.arange(rows)
+    for b in range(K // 64):
+        blk = h[:, 64 * b:64 * b + 64].reshape(rows, 8, 8)
+        for c in range(8):
+            out[b, r, c ^ (r & 7)] = blk[:, c]
+    return out.reshape(-1)
+
+
+def pack_decoder_tc(M, small):
+    """FP16 images for the tcgen05 engine + the FP32 small block, as bytes (uint8).  One image per layer serves the
+    forward pass (read K-major) and the reverse pass (read MN-major).  Input columns are duplicated (hi | lo halves)."""
+    W0, W1, W2, W3 = M["W0"], M["W1"], M["W2"], M["W3"]
+    w0 = np.concatenate([W0, W0], axis=1)                                   # (128, 64)
+    w3a = np.zeros((128, 128), np.float32); w3a[:, :96] = W3[:, :96]
+    w3b = np.concatenate([W3[:, 96:128], W3[:, 96:128]], axis=1)            # (128, 64)
+    imgs = [_swizzled_image(w0), _swizzled_image(W1), _swizzled_image(W2), _swizzled_image(w3a), _swizzled_image(w3b)]
+    img = np.concatenate(imgs).view(np.uint8)
+    assert img.size == 122880, img.size
+    sm = np.zeros(6144 // 4, np.float32); sm[:small.size] = small
+    return np.concatenate([img, sm.view(np.uint8)])
 
 
 def encoder_matrices(W):

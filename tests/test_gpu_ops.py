@@ -10,6 +10,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _fp32_engine():
+    """Exact-parity tests use the FP32 CUDA-core decoder engine; tests/test_gpu_tc.py covers the tcgen05 engine."""
+    lib = pkg()._lib.load()
+    lib.dfb_set_decoder_engine(0)
+    yield
+    lib.dfb_set_decoder_engine(1)
+
+
 def _depth_frame(H=240, W=320, seed=0):
     synth = pkg().synth
     seq = synth.SyntheticSequence(n_frames=1, H=H, W=W, seed=seed)

@@ -64,3 +64,30 @@ def test_encoder_blob_matches_oracle(dfb, weights):
     h2 = np.maximum(np.einsum("nk,gkj->ngj", h1, w2).reshape(-1, 256) + b2, 0)
     out = (h2 @ w3 + b3)[:, :29]
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_tc_images_follow_the_kernel_swizzle(dfb, weights):
+    """FP16 SWIZZLE_128B images of the tcgen05 engine: element (row, k) of a layer lives at
+    block (k // 64), row, 16-byte chunk ((k % 64) // 8) ^ (row & 7), lane k % 8 (csrc/decoder_tc.cu)."""
+    blob = dfb.weights.pack_decoder(weights)
+    assert blob.size == 91624 + 32256
+    tc = blob[91624:].view(np.uint8)
+    M = dfb.weights.decoder_matrices(weights)
+
+    def read(img_off, rows, K):
+        h = tc[img_off: img_off + rows * K * 2].view(np.float16).reshape(K // 64, rows, 8, 8)
+        out = np.zeros((rows, K), np.float16)
+        for r in range(rows):
+            for c in range(K // 8):
+                out[r, 8 * c: 8 * c + 8] = h[c // 8, r, (c % 8) ^ (r & 7)]
+        return out
+    w0 = read(0, 128, 64)
+    assert np.array_equal(w0[:, :32], M["W0"].astype(np.float16)) and np.array_equal(w0[:, 32:], M["W0"].astype(np.float16))
+    assert np.array_equal(read(16384, 128, 128), M["W1"].astype(np.float16))
+    assert np.array_equal(read(49152, 96, 128), M["W2"].astype(np.float16))
+    w3a = read(73728, 128, 128)
+    assert np.array_equal(w3a[:, :96], M["W3"][:, :96].astype(np.float16)) and not w3a[:, 96:].any()
+    w3b = read(106496, 128, 64)
+    assert np.array_equal(w3b[:, :32], M["W3"][:, 96:].astype(np.float16)) and np.array_equal(w3b[:, 32:], w3b[:, :32])
+    small = tc[122880:].view(np.float32)
+    assert np.array_equal(small[:1512], blob[90112:90112 + 1512])

@@ -148,6 +148,9 @@ def run_ours(args):
             d, c = (t.to(dev, non_blocking=True) for t in host_frames[i]) if e2e else frames[i]
             poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))
         trk.compute_sdf_Hg = timed_sdf
+        trk.time_kernels = True
+        trk.sdf_kernel_us = 0; trk.sdf_queries_J = 0; trk.sdf_queries_noJ = 0
+        n_sdf_before = trk.n_sdf_evals
         dfb._lib.CALLS.clear()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -173,10 +176,14 @@ def run_ours(args):
         launches = dfb._lib.kernel_launches()
         # dominant kernel: the fused SDF Gauss-Newton term
         dur, flops, n_launch = 0.0, 0.0, 0
-        for a, b, cnt, with_J in hg_events:
+        for a, b, cnt, with_J in hg_events:                 # Python-loop driver (native_gn = False)
             dur += a.elapsed_time(b) * 1e-3
             flops += cnt * (FLOP_FWD_BWD if with_J else FLOP_FWD)
             n_launch += 1
+        if trk.native_gn:                                    # C driver: events recorded around each SDF-term launch
+            dur = trk.sdf_kernel_us * 1e-6
+            flops = trk.sdf_queries_J * FLOP_FWD_BWD + trk.sdf_queries_noJ * FLOP_FWD
+            n_launch = trk.n_sdf_evals - n_sdf_before
         err_t = max(float(np.abs(p.t - seq.poses[i][1]).max()) for i, p in enumerate(poses))
         return dict(ms=ms, wall=wall, launches=launches, hg_time=dur, hg_flops=flops, hg_launches=n_launch, clocks=cs.summary(),
                     n_occupied=m.n_occupied, sdf_evals=trk.n_sdf_evals, rgb_evals=trk.n_rgb_evals, track_err=err_t,

@@ -174,6 +174,34 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
                const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
                const float* decoder_blob, int robust, float robust_k, int compute_J, double* out44, void* stream);
 
+/* SDFTracker.gauss_newton (tracker.py:225-288) as ONE host call: for every group of the iteration config, up to n_iter
+ * Gauss-Newton steps plus one evaluation-only pass, each evaluating the fused SDF term (dfb_sdf_hg) and/or the fused
+ * photometric term (dfb_rgb_hg), reading 44 doubles back, solving the 6x6 system and updating the pose in float64;
+ * a step whose energy rises is rolled back and ends its group (tracker.py:269-271).
+ * Poses are 12 doubles: R row-major (9) then t (3).  h_delta_pose is in/out (initial guess -> result).
+ * d_scratch80: device, 80 doubles.  h_pinned44: PINNED host memory, 44 doubles.
+ * h_stats[8] = {last value of the iteration counter (tracker.py:281), #sdf evaluations, #rgb evaluations, status, ...}.
+ * If h_stats[4] == 0x54494d45 on entry, the SDF-term launches are timed with CUDA events on `stream` and
+ * h_stats[4..6] return {microseconds, valid queries with reverse pass, valid queries forward-only}. */
+typedef struct {
+  int32_t n_groups;              /* <= 8 */
+  int32_t n_iter[8];             /* iter_config[i]["n"]                                  */
+  int32_t use_sdf[8];            /* group has an ['sdf'] term                             */
+  int32_t rgb_level[8];          /* pyramid level of its ['rgb', level] term, -1 = none   */
+  int32_t sdf_robust;  float sdf_robust_k;                       /* 0 none, 1 huber, 2 tukey */
+  int32_t rgb_robust;  float rgb_robust_k;
+  float rgb_weight, rgb_min_grad_scale, rgb_max_depth_delta;     /* fusion-lr-kt.yaml:51-56  */
+} dfb_gn_config;
+typedef struct {
+  const float* prev_I; const float* prev_D; const float* cur_I; const float* cur_D; const float* cur_G;
+  int32_t H, W;
+} dfb_rgb_level;
+int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n,
+                     const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
+                     const float* decoder_blob, const dfb_rgb_level* h_levels, const double* h_intr,
+                     const double* h_last_pose, double* h_delta_pose, double* d_scratch80, double* h_pinned44,
+                     int32_t* h_stats, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 5 -- meshing
  * ---------------------------------------------------------------------------------------------- */

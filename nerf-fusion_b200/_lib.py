@@ -22,6 +22,19 @@ class MapParams(C.Structure):
                 ("prune_min_vox_obs", C.c_int32), ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float)]
 
 
+class GnConfig(C.Structure):
+    """dfb_gn_config"""
+    _fields_ = [("n_groups", C.c_int32), ("n_iter", C.c_int32 * 8), ("use_sdf", C.c_int32 * 8), ("rgb_level", C.c_int32 * 8),
+                ("sdf_robust", C.c_int32), ("sdf_robust_k", C.c_float), ("rgb_robust", C.c_int32), ("rgb_robust_k", C.c_float),
+                ("rgb_weight", C.c_float), ("rgb_min_grad_scale", C.c_float), ("rgb_max_depth_delta", C.c_float)]
+
+
+class RgbLevel(C.Structure):
+    """dfb_rgb_level"""
+    _fields_ = [("prev_I", C.c_void_p), ("prev_D", C.c_void_p), ("cur_I", C.c_void_p), ("cur_D", C.c_void_p), ("cur_G", C.c_void_p),
+                ("H", C.c_int32), ("W", C.c_int32)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
@@ -58,6 +71,8 @@ SIGNATURES = {
     "dfb_decoder_forward": (_I, [_P, _I, _P, _P, _P, _P]),
     "dfb_get_sdf": (_I, [_MP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dfb_sdf_hg": (_I, [_MP, _P, _I, _FP, _P, _P, _P, _P, _I, _F, _I, _P, _P]),
+    "dfb_gauss_newton": (_I, [_MP, C.POINTER(GnConfig), _P, _I, _P, _P, _P, _P, C.POINTER(RgbLevel), C.POINTER(C.c_double),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.POINTER(C.c_int32), _P]),
     "dfb_decode_cubes_ws_bytes": (_SZ, [_I, _I]),
     "dfb_decode_cubes": (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
     "dfb_marching_cubes": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
@@ -68,7 +83,7 @@ KERNELS_PER_CALL = {
     "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 6,
     "dfb_point_box_filter": 14, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
     "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
-    "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
+    "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
 }
 CALLS = {}
 

@@ -66,6 +66,12 @@ class SDFTracker:
         self._hg_host = torch.zeros((80,), dtype=torch.float64).pin_memory()
         self.n_sdf_evals = 0
         self.n_rgb_evals = 0
+        # True: the whole Gauss-Newton solve of a frame is one C call (dfb_gauss_newton); False: the Python loop below
+        # (same control flow, kept for A/B tests and as executable documentation of tracker.py:225-288)
+        self.native_gn = True
+        self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
+        self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
+        self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()
 
     # ------------------------------------------------------------------------------------------ preprocessing
     def _make_image_pyramid(self, intensity_img, depth_img):
@@ -165,11 +171,69 @@ class SDFTracker:
         return H * error_scale, g * error_scale, float(e * error_scale)
 
     # ------------------------------------------------------------------------------------------ Gauss-Newton
+    def _gauss_newton_native(self, last_pose, delta_pose, Is, Ds, Gs, obs_xyz, calib):
+        from . import _lib
+        from ._lib import GnConfig, RgbLevel
+        m = self.map
+        cfg = GnConfig()
+        groups = self.args.iter_config
+        if len(groups) > 8:
+            raise ValueError("at most 8 iteration groups")
+        cfg.n_groups = len(groups)
+        need_rgb = False
+        for i, gcfg in enumerate(groups):
+            cfg.n_iter[i] = int(gcfg["n"])
+            cfg.use_sdf[i] = 0
+            cfg.rgb_level[i] = -1
+            for term in gcfg["type"]:
+                if term[0] == "sdf":
+                    cfg.use_sdf[i] = 1
+                elif term[0] == "rgb":
+                    cfg.rgb_level[i] = int(term[1]); need_rgb = True
+                else:
+                    raise NotImplementedError(term[0])
+        cfg.sdf_robust = _ROBUST[self.sdf_args.robust_kernel]; cfg.sdf_robust_k = float(self.sdf_args.robust_k)
+        cfg.rgb_robust = _ROBUST[self.rgb_args.robust_kernel]; cfg.rgb_robust_k = float(self.rgb_args.robust_k)
+        cfg.rgb_weight = float(self.rgb_args.weight); cfg.rgb_min_grad_scale = float(self.rgb_args.min_grad_scale)
+        cfg.rgb_max_depth_delta = float(self.rgb_args.max_depth_delta)
+        levels = (RgbLevel * 3)()
+        if need_rgb:
+            for l in range(3):
+                levels[l].prev_I = self.last_intensity[l].data_ptr(); levels[l].prev_D = self.last_depth[l].data_ptr()
+                levels[l].cur_I = Is[l].data_ptr(); levels[l].cur_D = Ds[l].data_ptr(); levels[l].cur_G = Gs[l].data_ptr()
+                levels[l].H, levels[l].W = int(Is[l].size(0)), int(Is[l].size(1))
+        intr = (C.c_double * 4)(calib.fx, calib.fy, calib.cx, calib.cy)
+        lastp = (C.c_double * 12)(*last_pose.q.rotation_matrix.reshape(-1).tolist(), *last_pose.t.tolist())
+        deltap = (C.c_double * 12)(*delta_pose.q.rotation_matrix.reshape(-1).tolist(), *delta_pose.t.tolist())
+        stats = (C.c_int32 * 8)()
+        if self.time_kernels:
+            stats[4] = 0x54494d45
+        obs = obs_xyz.contiguous()
+        with torch.cuda.device(m.device):
+            check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0), _p(m.indexer), _p(m.latent_vecs),
+                                         _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._hg_dev),
+                                         C.c_void_p(self._gn_pinned.data_ptr()), stats, _stream()))
+        self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
+        if self.time_kernels:
+            self.sdf_kernel_us += stats[4]; self.sdf_queries_J += stats[5]; self.sdf_queries_noJ += stats[6]
+        _lib.CALLS["dfb_sdf_hg"] = _lib.CALLS.get("dfb_sdf_hg", 0) + stats[1]      # launches made inside the C driver
+        _lib.CALLS["dfb_rgb_hg"] = _lib.CALLS.get("dfb_rgb_hg", 0) + stats[2]
+        d = np.array(list(deltap), dtype=np.float64)
+        new_delta = Isometry.from_matrix(d[:9].reshape(3, 3), d[9:12])
+        if stats[0] >= 10:
+            self.n_unstable += 1
+            if self.n_unstable >= 3:
+                self.rgb_args.weight = max(self.rgb_args.weight, 500.)
+        return last_pose.dot(new_delta)
+
     def gauss_newton(self, init_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz, calib):
         """tracker.py:225-288 (control flow unchanged: rollback+break when the energy rises, one evaluation-only pass per
         group, instability counter)."""
         last_pose = self.all_pd_pose[-1]
         cur_delta_pose = last_pose.inv().dot(init_pose)
+        if self.native_gn:
+            return self._gauss_newton_native(last_pose, cur_delta_pose, cur_intensity_pyramid, cur_depth_pyramid,
+                                             cur_dIdxy_pyramid, obs_xyz, calib)
         last_delta_pose = copy.deepcopy(cur_delta_pose)
         i_iter = 0
         for group in self.args.iter_config:

@@ -72,3 +72,30 @@ def test_track_and_integrate_matches_golden(weights, T):
         dR = np.abs(pose.q.rotation_matrix - T[f"f{i}_pose_R"]).max()
         assert dt < 2e-4 and dR < 2e-4, (i, dt, dR)
     assert trk.n_sdf_evals > 0 and trk.n_rgb_evals > 0
+
+
+def test_native_gauss_newton_equals_python_loop(weights, T):
+    """dfb_gauss_newton (one C call per frame) follows tracker.py:225-288 step for step: same poses as the Python loop."""
+    d = pkg()
+    poses = {}
+    for native in (False, True):
+        m = make_map(weights)
+        cfg = dict(TRACKING)
+        cfg["iter_config"] = [{"n": 3, "type": [["rgb", 2]]}, {"n": 3, "type": [["sdf"], ["rgb", 1]]}, {"n": 8, "type": [["sdf"], ["rgb", 0]]}]
+        trk = d.SDFTracker(m, ns(cfg))
+        trk.native_gn = native
+        calib = d.FrameIntrinsic(*T["calib"].tolist())
+        first = d.Isometry(q=d.Quaternion(array=d.synth.FIRST_TQ[3:]), t=np.array(d.synth.FIRST_TQ[:3]))
+        out = []
+        for i in range(3):
+            rgb, depth = _frame(T, i)
+            pose = trk.track_camera(rgb, depth, calib, first if i == 0 else None)
+            if i == 0:
+                pc, nrm = trk.last_processed_pc
+                m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+            out.append((pose.q.rotation_matrix.copy(), pose.t.copy()))
+        poses[native] = (out, trk.n_sdf_evals, trk.n_rgb_evals)
+    assert poses[True][1:] == poses[False][1:]                       # same number of evaluations = same accept/rollback path
+    for (Ra, ta), (Rb, tb) in zip(poses[True][0], poses[False][0]):
+        # both drivers cast the f64 poses to fp32 for the kernels; 1-ulp differences there are the only divergence
+        assert np.abs(Ra - Rb).max() < 1e-6 and np.abs(ta - tb).max() < 1e-6

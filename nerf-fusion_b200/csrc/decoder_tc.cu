@@ -21,7 +21,9 @@ namespace tc {
 
 constexpr int T = 128;          // query rows per tile = threads per tile group
 constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 warps, smem tiles, TMEM columns, barrier)
-constexpr int CTA_T = T * GROUPS;
+constexpr int HALVES = 2;       // warps 0-3 of a group own accumulator columns [0,64), warps 4-7 own [64,128) (same TMEM lanes)
+constexpr int GT = T * HALVES;  // threads per tile group
+constexpr int CTA_T = GT * GROUPS;
 // ---- blob (bytes): FP16 swizzled images + FP32 small block; packed by weights.pack_decoder_tc -------------------
 constexpr int IMG_W0 = 0;          // [128 rows x 64]: cols 0..31 = W0, cols 32..63 = W0 again (lo halves of the input)
 constexpr int IMG_W1 = 16384;      // 2 blocks x [128 x 64]
@@ -115,42 +117,62 @@ struct Ctx {
   uint32_t sa;        // same, shared-window address
   uint32_t tmem;      // TMEM address of this group's accumulator (lane 0)
   uint32_t tmem_base; // allocation base
-  int row, grp;       // row within the tile (= thread within the group), tile group
+  int row, half, grp; // row within the tile (= TMEM lane), column half owned by this thread, tile group
   uint32_t a_off, x_off;   // byte offsets of this group's activation / input tiles
   uint32_t mma_bar;   // shared address of the "MMA done" barrier
   uint32_t phase;     // its parity
-  uint32_t mask[4][4];
+  uint32_t mask[4][2];   // ReLU masks of this thread's 64 columns, per layer
 };
 
-// Thread 0 only.  K-major A (activation tile at a_addr, blocks of 16 KB), B = weight image at b_addr with b_rows rows per
-// 64-column block.  fwd: B read K-major; bwd: the same image read MN-major (k-step s = image rows 16s..16s+15).
-__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr, int b_rows, int ksteps, int N, bool bwd,
-                                      bool accumulate_first) {
-  const uint32_t idesc = instr_desc(N, bwd);
-  for (int s = 0; s < ksteps; ++s) {
-    const uint64_t ad = smem_desc(a_addr + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
-    const uint64_t bd = bwd ? smem_desc(b_addr + s * 2048, (uint32_t)b_rows * 128u, 1024)
-                            : smem_desc(b_addr + (s >> 2) * (b_rows * 128) + (s & 3) * 32, 16, 1024);
+// Issuing thread only.  K-major A (activation tile at a_addr, blocks of 16 KB), B = weight image at b_addr with B_ROWS rows
+// per 64-column block.  fwd: B read K-major; bwd: the same image read MN-major (k-step s = image rows 16s..16s+15).
+// Everything but the two base addresses is a compile-time constant, so each step is two 64-bit adds and one tcgen05.mma.
+template <int KSTEPS, int N, bool BWD, int B_ROWS>
+__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr, bool accumulate_first) {
+  constexpr uint32_t idesc = (1u << 4) | ((BWD ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
+  const uint64_t ad0 = smem_desc(a_addr, 16, 1024);
+  const uint64_t bd0 = BWD ? smem_desc(b_addr, (uint32_t)B_ROWS * 128u, 1024) : smem_desc(b_addr, 16, 1024);
+#pragma unroll
+  for (int s = 0; s < KSTEPS; ++s) {
+    const uint64_t ad = ad0 + (uint64_t)(((s >> 2) * 16384 + (s & 3) * 32) >> 4);
+    const uint64_t bd = bd0 + (uint64_t)((BWD ? s * 2048 : (s >> 2) * (B_ROWS * 128) + (s & 3) * 32) >> 4);
     mma_f16(c.tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
   }
 }
 
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(T) : "memory"); }
+#ifdef DFB_TC_PROFILE
+__device__ unsigned long long g_prof[256];
+__device__ int g_prof_n;
+#define PROF_MARK(c)                                                                         \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && (c).grp == 0 && (c).row == 0 && (c).half == 0) {                  \
+      int k_ = g_prof_n; if (k_ < 256) { g_prof[k_] = clock64(); g_prof_n = k_ + 1; }        \
+    }                                                                                        \
+  } while (0)
+#else
+#define PROF_MARK(c) do {} while (0)
+#endif
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
 
 // all threads of the group: make the tile writes visible to the tensor core, then thread 0 issues; everyone waits for completion
 #define TC_LAYER(ISSUE_STMTS)                         \
   do {                                                \
+    PROF_MARK(c);                                     \
     fence_proxy_async();                              \
     tc_fence_before();                                \
     group_sync(c.grp);                                \
-    if (c.row == 0) {                                 \
+    PROF_MARK(c);                                     \
+    if (c.row == 0 && c.half == 0) {                  \
       tc_fence_after();                               \
       ISSUE_STMTS;                                    \
       mma_commit(c.mma_bar);                          \
     }                                                 \
+    PROF_MARK(c);                                     \
     mbar_wait(c.mma_bar, c.phase);                    \
     c.phase ^= 1u;                                    \
     tc_fence_after();                                 \
+    PROF_MARK(c);                                     \
   } while (0)
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -170,25 +192,30 @@ __device__ __forceinline__ void store_cols32(uint8_t* tile, int row, int col0, c
   }
 }
 
-// hidden-layer forward epilogue: a = D + b, record [a > 0], write relu(a) as FP16 into the activation tile
+// hidden-layer forward epilogue for this thread's column half: a = D + b, record [a > 0], relu(a) -> FP16 activation tile
 template <int NCOLS>
 __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const int row = c.row;
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int j = 0; j < NCOLS / 32; ++j) {
-    float v[32];
-    tmem_ld32(tbase + j * 32, v);
-    uint32_t m = 0;
+  for (int jj = 0; jj < 2; ++jj) {
+    const int col0 = 64 * c.half + 32 * jj;
+    if (col0 < NCOLS) {                     // warp-uniform
+      float v[32];
+      tmem_ld32(tbase + col0, v);
+      uint32_t m = 0;
+      const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float a = v[i] + sm[bias_off + 32 * j + i];
-      m |= (a > 0.f ? 1u : 0u) << i;
-      v[i] = fmaxf(a, 0.f);
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 b = b4[i4];
+        const float a0 = v[4 * i4] + b.x, a1 = v[4 * i4 + 1] + b.y, a2 = v[4 * i4 + 2] + b.z, a3 = v[4 * i4 + 3] + b.w;
+        m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
+        v[4 * i4] = fmaxf(a0, 0.f); v[4 * i4 + 1] = fmaxf(a1, 0.f); v[4 * i4 + 2] = fmaxf(a2, 0.f); v[4 * i4 + 3] = fmaxf(a3, 0.f);
+      }
+      c.mask[layer][jj] = m;
+      store_cols32(c.sm + c.a_off, row, col0, v);
     }
-    c.mask[layer][j] = m;
-    store_cols32(c.sm + c.a_off, row, 32 * j, v);
   }
 }
 
@@ -198,103 +225,138 @@ __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
   const int row = c.row;
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int j = 0; j < NCOLS / 32; ++j) {
-    float v[32];
-    tmem_ld32(tbase + j * 32, v);
-    const uint32_t m = c.mask[layer][j];
+  for (int jj = 0; jj < 2; ++jj) {
+    const int col0 = 64 * c.half + 32 * jj;
+    if (col0 < NCOLS) {
+      float v[32];
+      tmem_ld32(tbase + col0, v);
+      const uint32_t m = c.mask[layer][jj];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
-    store_cols32(c.sm + c.a_off, row, 32 * j, v);
+      for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+      store_cols32(c.sm + c.a_off, row, col0, v);
+    }
   }
 }
 
-// write this thread's query (29 latent + 3 rel) as hi|lo FP16 halves into the input tile
+// the two threads of a row (column halves) combine partial sums through the (currently idle) input tile
+__device__ __forceinline__ void exchange(Ctx& c, float* vals, int nvals) {
+  float* ex = reinterpret_cast<float*>(c.sm + c.x_off);
+  for (int k = 0; k < nvals; ++k) ex[(c.half * T + c.row) * 4 + k] = vals[k];
+  group_sync(c.grp);
+  for (int k = 0; k < nvals; ++k) vals[k] = ex[c.row * 4 + k] + ex[(T + c.row) * 4 + k];   // fixed order: both threads get the same bits
+  group_sync(c.grp);
+}
+
+// write this row's query (29 latent + 3 rel) into the input tile: column half 0 stores the FP16 hi parts (cols 0..31),
+// half 1 the lo parts x - hi (cols 32..63)
 __device__ __forceinline__ void store_input(Ctx& c, const float* x32) {
-  float hi[32], lo[32];
+  float h[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    const float h = __half2float(__float2half_rn(x32[k]));
-    hi[k] = h;
-    lo[k] = x32[k] - h;
+    const float hi = __half2float(__float2half_rn(x32[k]));
+    h[k] = c.half == 0 ? hi : x32[k] - hi;
   }
-  store_cols32(c.sm + c.x_off, c.row, 0, hi);
-  store_cols32(c.sm + c.x_off, c.row, 32, lo);
+  store_cols32(c.sm + c.x_off, c.row, 32 * c.half, h);
 }
 
 // forward pass of the tile; returns pre-activation heads z (sdf) and u (std)
 __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  TC_LAYER(issue(c, c.sa + c.x_off, c.sa + IMG_W0, 128, 4, 128, false, false));
+  TC_LAYER((issue<4, 128, false, 128>(c, c.sa + c.x_off, c.sa + IMG_W0, false)));
   epi_fwd<128>(c, 0, DS_B0);
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W1, 128, 8, 128, false, false));
+  TC_LAYER((issue<8, 128, false, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));
   epi_fwd<128>(c, 1, DS_B1);
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W2, 96, 8, 96, false, false));
+  TC_LAYER((issue<8, 96, false, 96>(c, c.sa + c.a_off, c.sa + IMG_W2, false)));
   epi_fwd<96>(c, 2, DS_B2);
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W3A, 128, 8, 128, false, false);
-           issue(c, c.sa + c.x_off, c.sa + IMG_W3B, 128, 4, 128, false, true));
-  // heads in FP32 straight from the accumulator (h3 never leaves TMEM/registers)
+  TC_LAYER((issue<8, 128, false, 128>(c, c.sa + c.a_off, c.sa + IMG_W3A, false));
+           (issue<4, 128, false, 128>(c, c.sa + c.x_off, c.sa + IMG_W3B, true)));
+  // heads in FP32 straight from the accumulator (h3 never leaves TMEM/registers); each thread sums its 64 columns
   const int row = c.row;
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
-  float zz = sm[DS_B4], uu = sm[DS_B4 + 1];
+  float zu[2] = {0.f, 0.f};
+  float z1 = 0.f, u1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int jj = 0; jj < 2; ++jj) {
+    const int col0 = 64 * c.half + 32 * jj;
     float v[32];
-    tmem_ld32(tbase + j * 32, v);
+    tmem_ld32(tbase + col0, v);
     uint32_t m = 0;
+    const float4* b4 = reinterpret_cast<const float4*>(sm + DS_B3 + col0);
+    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + col0);
+    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float a = v[i] + sm[DS_B3 + 32 * j + i];
-      m |= (a > 0.f ? 1u : 0u) << i;
-      const float h = fmaxf(a, 0.f);
-      zz = fmaf(sm[DS_W4 + 32 * j + i], h, zz);
-      uu = fmaf(sm[DS_WU + 32 * j + i], h, uu);
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 b = b4[i4], wz = w4[i4], wv = wu[i4];
+      const float a0 = v[4 * i4] + b.x, a1 = v[4 * i4 + 1] + b.y, a2 = v[4 * i4 + 2] + b.z, a3 = v[4 * i4 + 3] + b.w;
+      m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
+      const float h0 = fmaxf(a0, 0.f), h1 = fmaxf(a1, 0.f), h2 = fmaxf(a2, 0.f), h3 = fmaxf(a3, 0.f);
+      zu[0] = fmaf(wz.x, h0, zu[0]); z1 = fmaf(wz.y, h1, z1); zu[0] = fmaf(wz.z, h2, zu[0]); z1 = fmaf(wz.w, h3, z1);
+      zu[1] = fmaf(wv.x, h0, zu[1]); u1 = fmaf(wv.y, h1, u1); zu[1] = fmaf(wv.z, h2, zu[1]); u1 = fmaf(wv.w, h3, u1);
     }
-    c.mask[3][j] = m;
+    c.mask[3][jj] = m;
   }
-  z = zz; u = uu;
+  zu[0] += z1; zu[1] += u1;
+  exchange(c, zu, 2);
+  z = zu[0] + sm[DS_B4]; u = zu[1] + sm[DS_B4 + 1];
 }
 
-// reverse pass: seeds on z and u -> d/d(xyz) in network units
+// reverse pass: seeds on z and u -> d/d(xyz) in network units (both threads of a row return the full sum)
 __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, float g[3]) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const int row = c.row;
-  float gx = 0.f, gy = 0.f, gz = 0.f;
+  float ga[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int jj = 0; jj < 2; ++jj) {
+    const int col0 = 64 * c.half + 32 * jj;
     float d[32];
-    const uint32_t m = c.mask[3][j];
+    const uint32_t m = c.mask[3][jj];
+    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + col0);
+    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + col0);
+    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W3X + 3 * col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int o = 32 * j + i;
-      const float dv = ((m >> i) & 1u) ? fmaf(seed_z, sm[DS_W4 + o], seed_u * sm[DS_WU + o]) : 0.f;
-      d[i] = dv;
-      gx = fmaf(sm[DS_W3X + 3 * o + 0], dv, gx);
-      gy = fmaf(sm[DS_W3X + 3 * o + 1], dv, gy);
-      gz = fmaf(sm[DS_W3X + 3 * o + 2], dv, gz);
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 wz = w4[i4], wv = wu[i4];
+      const float4 ta = t4[3 * i4], tb = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];     // taps of 4 consecutive units, 3 floats each
+      const uint32_t mm = m >> (4 * i4);
+      const float d0 = (mm & 1u) ? fmaf(seed_z, wz.x, seed_u * wv.x) : 0.f;
+      const float d1 = (mm & 2u) ? fmaf(seed_z, wz.y, seed_u * wv.y) : 0.f;
+      const float d2 = (mm & 4u) ? fmaf(seed_z, wz.z, seed_u * wv.z) : 0.f;
+      const float d3 = (mm & 8u) ? fmaf(seed_z, wz.w, seed_u * wv.w) : 0.f;
+      d[4 * i4] = d0; d[4 * i4 + 1] = d1; d[4 * i4 + 2] = d2; d[4 * i4 + 3] = d3;
+      ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
+      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb.x, d1, ga[1]); ga[2] = fmaf(tb.y, d1, ga[2]);
+      ga[0] = fmaf(tb.z, d2, ga[0]); ga[1] = fmaf(tb.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
+      ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
     }
-    store_cols32(c.sm + c.a_off, row, 32 * j, d);
+    store_cols32(c.sm + c.a_off, row, col0, d);
   }
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W3A, 128, 8, 128, true, false));   // delta2 = delta3 * W3[:, :96] (cols 96.. are 0)
+  TC_LAYER((issue<8, 128, true, 128>(c, c.sa + c.a_off, c.sa + IMG_W3A, false)));   // delta2 = delta3 * W3[:, :96] (cols 96.. are 0)
   epi_bwd<96>(c, 2);
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W2, 96, 6, 128, true, false));     // delta1 = delta2 * W2
+  TC_LAYER((issue<6, 128, true, 96>(c, c.sa + c.a_off, c.sa + IMG_W2, false)));     // delta1 = delta2 * W2
   epi_bwd<128>(c, 1);
-  TC_LAYER(issue(c, c.sa + c.a_off, c.sa + IMG_W1, 128, 8, 128, true, false));    // delta0 = delta1 * W1 (masked below)
+  TC_LAYER((issue<8, 128, true, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));    // delta0 = delta1 * W1 (masked below)
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int jj = 0; jj < 2; ++jj) {
+    const int col0 = 64 * c.half + 32 * jj;
     float v[32];
-    tmem_ld32(tbase + j * 32, v);
-    const uint32_t m = c.mask[0][j];
+    tmem_ld32(tbase + col0, v);
+    const uint32_t m = c.mask[0][jj];
+    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int o = 32 * j + i;
-      const float dv = ((m >> i) & 1u) ? v[i] : 0.f;
-      gx = fmaf(sm[DS_W0X + 3 * o + 0], dv, gx);
-      gy = fmaf(sm[DS_W0X + 3 * o + 1], dv, gy);
-      gz = fmaf(sm[DS_W0X + 3 * o + 2], dv, gz);
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 ta = t4[3 * i4], tb = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];
+      const uint32_t mm = m >> (4 * i4);
+      const float d0 = (mm & 1u) ? v[4 * i4] : 0.f, d1 = (mm & 2u) ? v[4 * i4 + 1] : 0.f;
+      const float d2 = (mm & 4u) ? v[4 * i4 + 2] : 0.f, d3 = (mm & 8u) ? v[4 * i4 + 3] : 0.f;
+      ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
+      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb.x, d1, ga[1]); ga[2] = fmaf(tb.y, d1, ga[2]);
+      ga[0] = fmaf(tb.z, d2, ga[0]); ga[1] = fmaf(tb.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
+      ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
     }
   }
-  g[0] = gx; g[1] = gy; g[2] = gz;
+  exchange(c, ga, 3);
+  g[0] = ga[0]; g[1] = ga[1]; g[2] = ga[2];
 }
 
 extern __shared__ unsigned char tc_smem_raw[];
@@ -306,8 +368,9 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   c.sm = tc_smem_raw + pad;
   c.sa = raw + pad;
   c.phase = 0;
+  c.grp = threadIdx.x / GT;
+  c.half = (threadIdx.x % GT) / T;
   c.row = threadIdx.x % T;
-  c.grp = threadIdx.x / T;
   c.a_off = SM_A + c.grp * SM_TILE_BYTES;
   c.x_off = c.a_off + SM_XOFF;
   const uint32_t wbar = c.sa + SM_BAR, slot = c.sa + SM_BAR + 48;
@@ -350,6 +413,44 @@ __device__ __forceinline__ void load_x(float* x32, const float* __restrict__ lat
   for (int k = 0; k < 3; ++k) x32[DFB_LATENT_DIM + k] = valid ? rel[k] : 0.f;
 }
 
+// the two threads of a row split the 29 Gauss-Newton sums: half 0 the 21 upper-triangle entries of J J^T, half 1 the rest
+__device__ __forceinline__ void hg_accumulate_half(float* acc, const float* J, float r, float w, bool with_J, int half) {
+  if (half == 0) {
+    if (with_J) {
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[t++] += w * J[a] * J[b];
+    }
+  } else {
+    if (with_J) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] += w * r * J[a];
+    }
+    acc[27] += w * r * r;
+    acc[28] += 1.0f;
+  }
+}
+
+// block_reduce_atomic with caller-provided shared scratch (the tile buffers are idle once the tile loop has ended)
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce_atomic_scratch(const float* vals, double* out, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double d = warp_sum((double)vals[k]);
+    if (lane == 0) red[w * NV + k] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < THREADS / 32; ++ww) s += red[ww * NV + threadIdx.x];
+    if (s != 0.0) atomicAdd(&out[threadIdx.x], s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restrict__ x, int n, const void* __restrict__ blob,
                                                         float* __restrict__ sdf, float* __restrict__ std_) {
@@ -363,7 +464,7 @@ __global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restr
     store_input(c, x32);
     float z, u;
     forward(c, z, u);
-    if (i < n) { sdf[i] = tanhf(z); std_[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (i < n && c.half == 0) { sdf[i] = tanhf(z); std_[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }
@@ -387,7 +488,7 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
     float z, u;
     forward(c, z, u);
     const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
-    if (i < n) {
+    if (i < n && c.half == 0) {
       valid_out[i] = valid ? 1 : 0;
       if (sdf) sdf[i] = valid ? s : 0.f;
       if (std_) std_[i] = valid ? sd : 0.f;
@@ -400,7 +501,7 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
       }
       float g[3];
       backward(c, gs, gu, g);
-      if (i < n) {
+      if (i < n && c.half == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) grad_xyz[3 * (size_t)i + a] = valid ? div_vs(g[a], M.vs, M.inv_vs, M.div_mode) : 0.f;
       }
@@ -436,6 +537,7 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
     forward(c, z, u);
     const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
     const float r = s / sd;
+    PROF_MARK(c);
     float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (with_J) {
       float g[3];
@@ -447,10 +549,10 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
         sdf_jacobian(P, gw, pc, J);
       }
     }
-    if (valid) hg_accumulate(acc, J, r, robust_w(r, robust, robust_k), with_J != 0);
+    if (valid) hg_accumulate_half(acc, J, r, robust_w(r, robust, robust_k), with_J != 0, c.half);
   }
   epilogue_free(c);
-  block_reduce_atomic<29, CTA_T>(acc, packed);
+  block_reduce_atomic_scratch<29, CTA_T>(acc, packed, reinterpret_cast<double*>(c.sm + SM_A));
 }
 
 __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int B, int r,
@@ -474,7 +576,7 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restr
     store_input(c, x32);
     float z, u;
     forward(c, z, u);
-    if (valid) { low_sdf[i] = tanhf(z); low_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (valid && c.half == 0) { low_sdf[i] = tanhf(z); low_std[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }
@@ -504,7 +606,7 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_refine_kernel(const float* __re
     store_input(c, x32);
     float z, u;
     forward(c, z, u);
-    if (valid) { cube_sdf[i] = -tanhf(z); cube_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (valid && c.half == 0) { cube_sdf[i] = -tanhf(z); cube_std[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }
@@ -515,9 +617,20 @@ static int prep(K kernel) {
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
   return DFB_OK;
 }
-static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, CTA_T), (long long)sm_count()); }
+static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, T * GROUPS), (long long)sm_count()); }
 
 }  // namespace tc
+
+#ifdef DFB_TC_PROFILE
+extern "C" int dfb_debug_read_prof(unsigned long long* h_out, int* h_n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h_n, tc::g_prof_n, sizeof(int));
+  cudaMemcpyFromSymbol(h_out, tc::g_prof, sizeof(unsigned long long) * 256);
+  int zero = 0;
+  cudaMemcpyToSymbol(tc::g_prof_n, &zero, sizeof(int));
+  return 0;
+}
+#endif
 
 int tc_decoder_explicit(const float* x, int n, const void* blob, float* sdf, float* std_, cudaStream_t s) {
   int rc = tc::prep(tc::explicit_kernel);

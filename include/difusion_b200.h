@@ -88,6 +88,17 @@ int dfb_point_box_filter(const float* points, const float* normals, int n, float
                          float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
                          void* stream);
 
+/* The geometry half of SDFTracker.track_camera (tracker.py:89-120) as ONE asynchronous call with no host
+ * synchronisation: nearest x0.5 subsample of the (H,W) depth (NaN = invalid), unproject with halved intrinsics, drop
+ * invalid pixels, radius-outlier filter, PCA normals, drop NaN normals, 2 cm box filter.  Compactions keep row order
+ * (like the reference's boolean-mask indexing), intermediate counts stay on the device.  out_points/out_normals hold up
+ * to (H/2)*(W/2) rows; *d_n_out (device int32) receives the number of rows (-1: box-filter key range overflow). */
+size_t dfb_preprocess_ws_bytes(int H, int W);
+int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, float cx, float cy, int nb_points,
+                         float outlier_radius, int max_nn, float normal_radius, const float* h_cam_xyz, float box_voxel,
+                         int div_mode, float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* system.ext.groupby_sum (indexing.cpp:3-4, indexing.cu:59-71,89-109): sum (C,L) f32 and count (C,) i32 of
  * values (n,L) grouped by indices (n,) i64.  Outputs are zeroed here.  Like the reference kernel, `count` is
  * incremented once per element, i.e. it holds L x (number of rows in the group). */

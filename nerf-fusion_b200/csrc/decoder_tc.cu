@@ -21,8 +21,11 @@ namespace tc {
 
 constexpr int T = 128;          // query rows per tile = threads per tile group
 constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 warps, smem tiles, TMEM columns, barrier)
-constexpr int HALVES = 2;       // warps 0-3 of a group own accumulator columns [0,64), warps 4-7 own [64,128) (same TMEM lanes)
-constexpr int GT = T * HALVES;  // threads per tile group
+constexpr int NPART = 2;        // threads per row: part p owns accumulator columns [CW p, CW p + CW) (warps 4p..4p+3 of the group; same TMEM
+                                // lanes).  Measured on B200 at 2^24 queries: NPART=2 1.42 G q/s, NPART=4 1.14 G q/s (barrier + redundant
+                                // front-end cost outweighs the extra warps)
+constexpr int CW = 128 / NPART; // accumulator columns per thread
+constexpr int GT = T * NPART;   // threads per tile group
 constexpr int CTA_T = GT * GROUPS;
 // ---- blob (bytes): FP16 swizzled images + FP32 small block; packed by weights.pack_decoder_tc -------------------
 constexpr int IMG_W0 = 0;          // [128 rows x 64]: cols 0..31 = W0, cols 32..63 = W0 again (lo halves of the input)
@@ -117,11 +120,11 @@ struct Ctx {
   uint32_t sa;        // same, shared-window address
   uint32_t tmem;      // TMEM address of this group's accumulator (lane 0)
   uint32_t tmem_base; // allocation base
-  int row, half, grp; // row within the tile (= TMEM lane), column half owned by this thread, tile group
+  int row, part, grp; // row within the tile (= TMEM lane), column part owned by this thread, tile group
   uint32_t a_off, x_off;   // byte offsets of this group's activation / input tiles
   uint32_t mma_bar;   // shared address of the "MMA done" barrier
   uint32_t phase;     // its parity
-  uint32_t mask[4][2];   // ReLU masks of this thread's 64 columns, per layer
+  uint32_t mask[4][CW / 32];   // ReLU masks of this thread's columns, per layer
 };
 
 // Issuing thread only.  K-major A (activation tile at a_addr, blocks of 16 KB), B = weight image at b_addr with B_ROWS rows
@@ -163,7 +166,7 @@ __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0,
     tc_fence_before();                                \
     group_sync(c.grp);                                \
     PROF_MARK(c);                                     \
-    if (c.row == 0 && c.half == 0) {                  \
+    if (c.row == 0 && c.part == 0) {                  \
       tc_fence_after();                               \
       ISSUE_STMTS;                                    \
       mma_commit(c.mma_bar);                          \
@@ -199,8 +202,8 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
   const int row = c.row;
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = 64 * c.half + 32 * jj;
+  for (int jj = 0; jj < CW / 32; ++jj) {
+    const int col0 = CW * c.part + 32 * jj;
     if (col0 < NCOLS) {                     // warp-uniform
       float v[32];
       tmem_ld32(tbase + col0, v);
@@ -225,8 +228,8 @@ __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
   const int row = c.row;
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = 64 * c.half + 32 * jj;
+  for (int jj = 0; jj < CW / 32; ++jj) {
+    const int col0 = CW * c.part + 32 * jj;
     if (col0 < NCOLS) {
       float v[32];
       tmem_ld32(tbase + col0, v);
@@ -241,22 +244,41 @@ __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
 // the two threads of a row (column halves) combine partial sums through the (currently idle) input tile
 __device__ __forceinline__ void exchange(Ctx& c, float* vals, int nvals) {
   float* ex = reinterpret_cast<float*>(c.sm + c.x_off);
-  for (int k = 0; k < nvals; ++k) ex[(c.half * T + c.row) * 4 + k] = vals[k];
+  for (int k = 0; k < nvals; ++k) ex[(c.part * T + c.row) * 4 + k] = vals[k];
   group_sync(c.grp);
-  for (int k = 0; k < nvals; ++k) vals[k] = ex[c.row * 4 + k] + ex[(T + c.row) * 4 + k];   // fixed order: both threads get the same bits
+  for (int k = 0; k < nvals; ++k) {
+    float sacc = ex[c.row * 4 + k];
+#pragma unroll
+    for (int p = 1; p < NPART; ++p) sacc += ex[(p * T + c.row) * 4 + k];   // fixed order: all threads of the row get the same bits
+    vals[k] = sacc;
+  }
   group_sync(c.grp);
 }
 
-// write this row's query (29 latent + 3 rel) into the input tile: column half 0 stores the FP16 hi parts (cols 0..31),
-// half 1 the lo parts x - hi (cols 32..63)
-__device__ __forceinline__ void store_input(Ctx& c, const float* x32) {
-  float h[32];
+// Write this row's query (29 latent + 3 rel) into the input tile [hi(32) | lo(32)]: each of the NPART threads of the row
+// stores XC = 64 / NPART consecutive columns (FP16 hi parts in columns 0..31, x - hi in 32..63).
+constexpr int XC = 64 / NPART;
+__device__ __forceinline__ void store_input(Ctx& c, const float* __restrict__ latent_row, const float rel[3], bool valid) {
+  const int col_begin = XC * c.part;
+  const bool lo = col_begin >= 32;
+  const int k0 = col_begin & 31;
+  float h[XC];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float hi = __half2float(__float2half_rn(x32[k]));
-    h[k] = c.half == 0 ? hi : x32[k] - hi;
+  for (int i = 0; i < XC; ++i) {
+    const int k = k0 + i;
+    float x = 0.f;
+    if (valid) x = k < DFB_LATENT_DIM ? __ldg(latent_row + k) : (k == DFB_LATENT_DIM ? rel[0] : (k == DFB_LATENT_DIM + 1 ? rel[1] : rel[2]));
+    const float hi = __half2float(__float2half_rn(x));
+    h[i] = lo ? x - hi : hi;
   }
-  store_cols32(c.sm + c.x_off, c.row, 32 * c.half, h);
+#pragma unroll
+  for (int q = 0; q < XC / 8; ++q) {
+    const int chunk = (col_begin >> 3) + q;
+    uint4 v;
+    v.x = pack_h2(h[8 * q + 0], h[8 * q + 1]); v.y = pack_h2(h[8 * q + 2], h[8 * q + 3]);
+    v.z = pack_h2(h[8 * q + 4], h[8 * q + 5]); v.w = pack_h2(h[8 * q + 6], h[8 * q + 7]);
+    *reinterpret_cast<uint4*>(c.sm + c.x_off + c.row * 128 + (((chunk & 7) ^ (c.row & 7)) << 4)) = v;
+  }
 }
 
 // forward pass of the tile; returns pre-activation heads z (sdf) and u (std)
@@ -276,8 +298,8 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   float zu[2] = {0.f, 0.f};
   float z1 = 0.f, u1 = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = 64 * c.half + 32 * jj;
+  for (int jj = 0; jj < CW / 32; ++jj) {
+    const int col0 = CW * c.part + 32 * jj;
     float v[32];
     tmem_ld32(tbase + col0, v);
     uint32_t m = 0;
@@ -306,8 +328,8 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
   const int row = c.row;
   float ga[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = 64 * c.half + 32 * jj;
+  for (int jj = 0; jj < CW / 32; ++jj) {
+    const int col0 = CW * c.part + 32 * jj;
     float d[32];
     const uint32_t m = c.mask[3][jj];
     const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + col0);
@@ -337,8 +359,8 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
   TC_LAYER((issue<8, 128, true, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));    // delta0 = delta1 * W1 (masked below)
   const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const int col0 = 64 * c.half + 32 * jj;
+  for (int jj = 0; jj < CW / 32; ++jj) {
+    const int col0 = CW * c.part + 32 * jj;
     float v[32];
     tmem_ld32(tbase + col0, v);
     const uint32_t m = c.mask[0][jj];
@@ -369,7 +391,7 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   c.sa = raw + pad;
   c.phase = 0;
   c.grp = threadIdx.x / GT;
-  c.half = (threadIdx.x % GT) / T;
+  c.part = (threadIdx.x % GT) / T;
   c.row = threadIdx.x % T;
   c.a_off = SM_A + c.grp * SM_TILE_BYTES;
   c.x_off = c.a_off + SM_XOFF;
@@ -413,41 +435,51 @@ __device__ __forceinline__ void load_x(float* x32, const float* __restrict__ lat
   for (int k = 0; k < 3; ++k) x32[DFB_LATENT_DIM + k] = valid ? rel[k] : 0.f;
 }
 
-// the two threads of a row split the 29 Gauss-Newton sums: half 0 the 21 upper-triangle entries of J J^T, half 1 the rest
-__device__ __forceinline__ void hg_accumulate_half(float* acc, const float* J, float r, float w, bool with_J, int half) {
-  if (half == 0) {
-    if (with_J) {
-      int t = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[t++] += w * J[a] * J[b];
-    }
-  } else {
-    if (with_J) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] += w * r * J[a];
-    }
-    acc[27] += w * r * r;
-    acc[28] += 1.0f;
+// The NPART threads of a row split the 29 Gauss-Newton sums (21 upper-triangle J J^T, 6 J r, energy, count): part p keeps
+// packed entries [8p, 8p+8) in acc[8].
+__device__ __forceinline__ void hg_accumulate_case(float* acc8, const float* J, float r, float w, bool with_J, int which) {
+  switch (which) {   // static indices inside each case
+    case 0:
+      if (with_J) { acc8[0] += w * J[0] * J[0]; acc8[1] += w * J[0] * J[1]; acc8[2] += w * J[0] * J[2]; acc8[3] += w * J[0] * J[3];
+                    acc8[4] += w * J[0] * J[4]; acc8[5] += w * J[0] * J[5]; acc8[6] += w * J[1] * J[1]; acc8[7] += w * J[1] * J[2]; }
+      break;
+    case 1:
+      if (with_J) { acc8[0] += w * J[1] * J[3]; acc8[1] += w * J[1] * J[4]; acc8[2] += w * J[1] * J[5]; acc8[3] += w * J[2] * J[2];
+                    acc8[4] += w * J[2] * J[3]; acc8[5] += w * J[2] * J[4]; acc8[6] += w * J[2] * J[5]; acc8[7] += w * J[3] * J[3]; }
+      break;
+    case 2:
+      if (with_J) { acc8[0] += w * J[3] * J[4]; acc8[1] += w * J[3] * J[5]; acc8[2] += w * J[4] * J[4]; acc8[3] += w * J[4] * J[5];
+                    acc8[4] += w * J[5] * J[5]; acc8[5] += w * r * J[0]; acc8[6] += w * r * J[1]; acc8[7] += w * r * J[2]; }
+      break;
+    default:
+      if (with_J) { acc8[0] += w * r * J[3]; acc8[1] += w * r * J[4]; acc8[2] += w * r * J[5]; }
+      acc8[3] += w * r * r;
+      acc8[4] += 1.0f;
+      break;
   }
 }
 
-// block_reduce_atomic with caller-provided shared scratch (the tile buffers are idle once the tile loop has ended)
-template <int NV, int THREADS>
-__device__ __forceinline__ void block_reduce_atomic_scratch(const float* vals, double* out, double* red) {
+constexpr int HG_PER_THREAD = 32 / NPART;   // packed entries kept by one thread (4 / NPART cases of 8)
+__device__ __forceinline__ void hg_accumulate_part(float* acc, const float* J, float r, float w, bool with_J, int part) {
+#pragma unroll
+  for (int sub = 0; sub < 4 / NPART; ++sub) hg_accumulate_case(acc + 8 * sub, J, r, w, with_J, part * (4 / NPART) + sub);
+}
+
+// CTA reduction of the per-part partial sums into the packed 29 doubles (scratch: idle tile buffers)
+__device__ __forceinline__ void block_reduce_parts(const float* acc8, int part, double* out, double* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double d = warp_sum((double)vals[k]);
-    if (lane == 0) red[w * NV + k] = d;
+  for (int k = 0; k < HG_PER_THREAD; ++k) {
+    const double d = warp_sum((double)acc8[k]);
+    if (lane == 0) red[w * HG_PER_THREAD + k] = d;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
-    double s = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < THREADS / 32; ++ww) s += red[ww * NV + threadIdx.x];
-    if (s != 0.0) atomicAdd(&out[threadIdx.x], s);
+  if (threadIdx.x < 29) {
+    const int p = threadIdx.x / HG_PER_THREAD, k = threadIdx.x % HG_PER_THREAD;
+    double sacc = 0.0;
+    for (int ww = 0; ww < CTA_T / 32; ++ww)
+      if (((ww * 32) % GT) / T == p) sacc += red[ww * HG_PER_THREAD + k];
+    if (sacc != 0.0) atomicAdd(&out[threadIdx.x], sacc);
   }
 }
 
@@ -458,13 +490,14 @@ __global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restr
   prologue(c, blob);
   for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
     const int i = (int)(tile * T) + c.row;
-    float x32[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) x32[k] = i < n ? x[(size_t)i * 32 + k] : 0.f;
-    store_input(c, x32);
+    {
+      const float* xr = x + (size_t)(i < n ? i : 0) * 32;
+      const float rel3[3] = {i < n ? xr[29] : 0.f, i < n ? xr[30] : 0.f, i < n ? xr[31] : 0.f};
+      store_input(c, xr, rel3, i < n);
+    }
     float z, u;
     forward(c, z, u);
-    if (i < n && c.half == 0) { sdf[i] = tanhf(z); std_[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (i < n && c.part == 0) { sdf[i] = tanhf(z); std_[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }
@@ -482,13 +515,11 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
     long long slot = 0;
     float rel[3] = {0.f, 0.f, 0.f};
     if (i < n) valid = map_lookup(M, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], indexer, obs_count, slot, rel);
-    float x32[32];
-    load_x(x32, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
-    store_input(c, x32);
+    store_input(c, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
     float z, u;
     forward(c, z, u);
     const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
-    if (i < n && c.half == 0) {
+    if (i < n && c.part == 0) {
       valid_out[i] = valid ? 1 : 0;
       if (sdf) sdf[i] = valid ? s : 0.f;
       if (std_) std_[i] = valid ? sd : 0.f;
@@ -501,7 +532,7 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
       }
       float g[3];
       backward(c, gs, gu, g);
-      if (i < n && c.half == 0) {
+      if (i < n && c.part == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) grad_xyz[3 * (size_t)i + a] = valid ? div_vs(g[a], M.vs, M.inv_vs, M.div_mode) : 0.f;
       }
@@ -516,9 +547,9 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
                                                       float robust_k, int with_J, double* __restrict__ packed) {
   Ctx c;
   prologue(c, blob);
-  float acc[29];
+  float acc[HG_PER_THREAD];
 #pragma unroll
-  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+  for (int k = 0; k < HG_PER_THREAD; ++k) acc[k] = 0.f;
   for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
     const int i = (int)(tile * T) + c.row;
     bool valid = false;
@@ -530,9 +561,7 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
       xform(P.Rt, P.tt, pc[0], pc[1], pc[2], pw);
       valid = map_lookup(M, pw[0], pw[1], pw[2], indexer, obs_count, slot, rel);
     }
-    float x32[32];
-    load_x(x32, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
-    store_input(c, x32);
+    store_input(c, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
     float z, u;
     forward(c, z, u);
     const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
@@ -549,10 +578,10 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
         sdf_jacobian(P, gw, pc, J);
       }
     }
-    if (valid) hg_accumulate_half(acc, J, r, robust_w(r, robust, robust_k), with_J != 0, c.half);
+    if (valid) hg_accumulate_part(acc, J, r, robust_w(r, robust, robust_k), with_J != 0, c.part);
   }
   epilogue_free(c);
-  block_reduce_atomic_scratch<29, CTA_T>(acc, packed, reinterpret_cast<double*>(c.sm + SM_A));
+  block_reduce_parts(acc, c.part, packed, reinterpret_cast<double*>(c.sm + SM_A));
 }
 
 __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int B, int r,
@@ -571,12 +600,10 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restr
       rel[0] = lattice(cc / (r * r), vsize, a); rel[1] = lattice((cc / r) % r, vsize, a); rel[2] = lattice(cc % r, vsize, a);
       slot = occ[b];
     }
-    float x32[32];
-    load_x(x32, latents + slot * DFB_LATENT_DIM, rel, valid);
-    store_input(c, x32);
+    store_input(c, latents + slot * DFB_LATENT_DIM, rel, valid);
     float z, u;
     forward(c, z, u);
-    if (valid && c.half == 0) { low_sdf[i] = tanhf(z); low_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (valid && c.part == 0) { low_sdf[i] = tanhf(z); low_std[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }
@@ -601,12 +628,10 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_refine_kernel(const float* __re
       rel[0] = lattice(cc / (R * R), vsize, a); rel[1] = lattice((cc / R) % R, vsize, a); rel[2] = lattice(cc % R, vsize, a);
       slot = occ[b];
     }
-    float x32[32];
-    load_x(x32, latents + slot * DFB_LATENT_DIM, rel, valid);
-    store_input(c, x32);
+    store_input(c, latents + slot * DFB_LATENT_DIM, rel, valid);
     float z, u;
     forward(c, z, u);
-    if (valid && c.half == 0) { cube_sdf[i] = -tanhf(z); cube_std[i] = 0.05f + 0.5f * softplus_torch(u); }
+    if (valid && c.part == 0) { cube_sdf[i] = -tanhf(z); cube_std[i] = 0.05f + 0.5f * softplus_torch(u); }
   }
   epilogue_free(c);
 }

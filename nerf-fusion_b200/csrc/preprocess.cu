@@ -68,7 +68,8 @@ __global__ void bbox_init_kernel(unsigned* bbox) {
   else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
 }
 
-__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, int n, int stride, unsigned* bbox) {
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, int n, int stride, unsigned* bbox, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -125,7 +126,8 @@ __device__ __forceinline__ int3 cell_coord(const GridParams& g, float x, float y
 }
 
 __global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict__ pc4, int n, const GridParams* gpp,
-                                                         int* cell_of, int* cell_count) {
+                                                         int* cell_of, int* cell_count, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   GridParams g = *gpp;
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restrict__ pc4, int n, const int* cell_of,
-                                                           const int* cell_start, int* cursor, float4* sorted) {
+                                                           const int* cell_start, int* cursor, float4* sorted, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = reinterpret_cast<const float4*>(pc4)[i];
@@ -154,7 +157,9 @@ __device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, f
 
 __global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restrict__ sorted, int n,
                                                            const GridParams* gpp, const int* __restrict__ cell_start,
-                                                           int nb_points, float radius, uint8_t* __restrict__ mask) {
+                                                           int nb_points, float radius, uint8_t* __restrict__ mask,
+                                                           const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   GridParams g = *gpp;
@@ -220,7 +225,8 @@ __device__ float4 sym3eig_smallest(float3 x1, float3 x2, float3 x3) {
 template <int K>
 __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ sorted, int n, const GridParams* gpp,
                                                       const int* __restrict__ cell_start, int max_nn, float radius,
-                                                      float3 cam, float* __restrict__ normals) {
+                                                      float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   GridParams g = *gpp;
@@ -294,17 +300,17 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   normals[3 * oi + 2] = nrm.z;
 }
 
-static int build_grid(const float* pc4, int n, float radius, GridWs& w, cudaStream_t s) {
+static int build_grid(const float* pc4, int n, float radius, GridWs& w, cudaStream_t s, const int* n_dev = nullptr) {
   bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
-  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox);
+  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
   grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, radius, w.gp);
   DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
-  grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count);
+  grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev);
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_i32(w.cell_count, w.cell_start, GRID_CAP + 1, w.block_sums, nullptr, s);
   if (rc) return rc;
   DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
-  grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted);
+  grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -313,7 +319,8 @@ static int build_grid(const float* pc4, int n, float radius, GridWs& w, cudaStre
 // scatter_mean / box filter: deterministic segmented mean
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) seg_count_kernel(const int64_t* __restrict__ index64, const int* __restrict__ index32,
-                                                        int n, int* seg_count) {
+                                                        int n, int* seg_count, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int g = index64 ? (int)index64[i] : index32[i];
@@ -321,7 +328,9 @@ __global__ void __launch_bounds__(256) seg_count_kernel(const int64_t* __restric
 }
 
 __global__ void __launch_bounds__(256) seg_fill_kernel(const int64_t* __restrict__ index64, const int* __restrict__ index32,
-                                                       int n, const int* seg_start, int* cursor, int* members) {
+                                                       int n, const int* seg_start, int* cursor, int* members,
+                                                       const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int g = index64 ? (int)index64[i] : index32[i];
@@ -403,6 +412,7 @@ __global__ void box_params_kernel(const unsigned* bbox, float voxel_size, int di
   float mn[3], ext[3];
   for (int a = 0; a < 3; ++a) {
     float lo = ord2f(bbox[a]), hi = ord2f(bbox[3 + a]);
+    if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }       // empty input (the fused path may legitimately have 0 rows)
     mn[a] = __fsub_rn(lo, half);
     float mx = __fadd_rn(hi, half);
     ext[a] = floorf(div_vs(__fsub_rn(mx, mn[a]), voxel_size, inv, div_mode));
@@ -417,7 +427,8 @@ __global__ void box_params_kernel(const unsigned* bbox, float voxel_size, int di
 
 __global__ void __launch_bounds__(256) box_key_kernel(const float* __restrict__ pts, int n, float voxel_size,
                                                       int div_mode, const BoxParams* bpp, long long* keys,
-                                                      uint32_t* bits) {
+                                                      uint32_t* bits, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   BoxParams bp = *bpp;
@@ -434,7 +445,8 @@ __global__ void __launch_bounds__(256) box_key_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) box_rank_kernel(const long long* __restrict__ keys, int n,
                                                        const uint32_t* __restrict__ bits, const int* __restrict__ word_rank,
-                                                       const BoxParams* bpp, int* rank_out) {
+                                                       const BoxParams* bpp, int* rank_out, const int* __restrict__ n_dev) {
+  if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (bpp->overflow) { rank_out[i] = 0; return; }
@@ -459,6 +471,54 @@ __global__ void __launch_bounds__(256) groupby_sum_kernel(const float* __restric
   if (g < 0 || g >= C) return;
   atomicAdd(&sum[g * L + l], values[t]);
   if (l == 0) atomicAdd(&count[g], L);   // the reference bumps the count once per ELEMENT (indexing.cu:69-70), i.e. L per row
+}
+
+// ---- fused preprocessing helpers -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unproject_sub_kernel(const float* __restrict__ depth, int H, int W, int Hs, int Ws, float fx, float fy,
+                                                            float cx, float cy, float* __restrict__ pc4, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Hs * Ws) return;
+  const int v = i / Ws, u = i - v * Ws;
+  const float d = depth[(size_t)(2 * v) * W + 2 * u];       // F.interpolate(scale 0.5, nearest) == depth[2v][2u]
+  const bool ok = !isnan(d);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) { p.x = ((float)u - cx) / fx * d; p.y = ((float)v - cy) / fy * d; p.z = d; }
+  reinterpret_cast<float4*>(pc4)[i] = p;
+  flag[i] = ok ? 1 : 0;
+}
+
+// order-preserving compaction (the reference's boolean-mask indexing keeps row order, tracker.py:104-116)
+__global__ void __launch_bounds__(256) compact4_kernel(const float* __restrict__ in4, const int* __restrict__ flag, const int* __restrict__ pos,
+                                                       int n, const int* __restrict__ n_dev, float* __restrict__ out4) {
+  if (n_dev) n = *n_dev;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  reinterpret_cast<float4*>(out4)[pos[i]] = reinterpret_cast<const float4*>(in4)[i];
+}
+
+__global__ void __launch_bounds__(256) flag_from_mask_kernel(const uint8_t* __restrict__ mask, int n_max, const int* __restrict__ n_dev,
+                                                             int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max) return;
+  flag[i] = (i < *n_dev && mask[i]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) flag_from_normals_kernel(const float* __restrict__ nrm, int n_max, const int* __restrict__ n_dev,
+                                                                int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max) return;
+  flag[i] = (i < *n_dev && !isnan(nrm[3 * (size_t)i])) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) compact_pn_kernel(const float* __restrict__ pc4, const float* __restrict__ nrm, const int* __restrict__ flag,
+                                                         const int* __restrict__ pos, int n, const int* __restrict__ n_dev,
+                                                         float* __restrict__ p3, float* __restrict__ n3) {
+  if (n_dev) n = *n_dev;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int o = pos[i];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { p3[3 * (size_t)o + a] = pc4[4 * (size_t)i + a]; n3[3 * (size_t)o + a] = nrm[3 * (size_t)i + a]; }
 }
 
 }  // namespace dfb
@@ -495,7 +555,7 @@ int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radi
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
   int rc = build_grid(pc4, n, radius, w, s);
   if (rc) return rc;
-  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask);
+  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask, nullptr);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -514,9 +574,9 @@ int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, cons
   if (rc) return rc;
   float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16)
-    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals);
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
   else
-    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals);
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -529,7 +589,8 @@ size_t dfb_scatter_mean_ws_bytes(int n, int n_out) {
 }
 
 static int segmented_mean(const float* srcA, const float* srcB, const int64_t* index64, const int* index32, int n, int d,
-                          int n_out_cap, const int* n_out_dev, float* outA, float* outB, Arena& a, cudaStream_t s) {
+                          int n_out_cap, const int* n_out_dev, float* outA, float* outB, Arena& a, cudaStream_t s,
+                          const int* n_dev = nullptr) {
   int* seg_count = a.take<int>(n_out_cap + 2);
   int* seg_start = a.take<int>(n_out_cap + 2);
   int* cursor = a.take<int>(n_out_cap + 2);
@@ -538,11 +599,11 @@ static int segmented_mean(const float* srcA, const float* srcB, const int64_t* i
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
   DFB_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int) * (n_out_cap + 2), s));
   DFB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (n_out_cap + 2), s));
-  seg_count_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_count);
+  seg_count_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_count, n_dev);
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_i32(seg_count, seg_start, n_out_cap + 1, bsums, nullptr, s);
   if (rc) return rc;
-  seg_fill_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_start, cursor, members);
+  seg_fill_kernel<<<div_up(n, 256), 256, 0, s>>>(index64, index32, n, seg_start, cursor, members, n_dev);
   if (d == 3)
     seg_mean_kernel<3><<<div_up(n_out_cap, 128), 128, 0, s>>>(srcA, srcB, seg_start, members, n_out_dev, n_out_cap, outA, outB);
   else {
@@ -569,14 +630,8 @@ size_t dfb_box_filter_ws_bytes(int n) {
   return a.off + dfb_scatter_mean_ws_bytes(n, n) + 256;
 }
 
-int dfb_point_box_filter(const float* points, const float* normals, int n, float voxel_size, int div_mode,
-                         float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
-                         void* stream) {
-  DFB_CHECK_ARG(n >= 0 && voxel_size > 0.f && d_n_out, "point_box_filter");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (n == 0) { DFB_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), s)); return DFB_OK; }
-  DFB_CHECK_ARG(points && normals && out_points && out_normals && ws, "point_box_filter: null pointer");
-  Arena a(ws, ws_bytes);
+static int box_filter_impl(const float* points, const float* normals, int n, const int* n_dev, float voxel_size, int div_mode,
+                           float* out_points, float* out_normals, int32_t* d_n_out, Arena& a, cudaStream_t s) {
   unsigned* bbox = a.take<unsigned>(8);
   BoxParams* bp = a.take<BoxParams>(1);
   long long* keys = a.take<long long>(n + 1);
@@ -586,23 +641,100 @@ int dfb_point_box_filter(const float* points, const float* normals, int n, float
   int* bsums = a.take<int>(max_words / 2048 + 8);
   int* rank = a.take<int>(n + 1);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  // The bitmap is kept all-zero between calls (first use: the caller hands in zeroed memory or we clear it here
-  // once per call for the words a frame can touch -- we clear everything the key range may address).
   bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
-  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(points, n, 3, bbox);
+  bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(points, n, 3, bbox, n_dev);
   box_params_kernel<<<1, 1, 0, s>>>(bbox, voxel_size, div_mode, bp);
   DFB_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)(max_words + 1), s));
-  box_key_kernel<<<div_up(n, 256), 256, 0, s>>>(points, n, voxel_size, div_mode, bp, keys, bits);
+  box_key_kernel<<<div_up(n, 256), 256, 0, s>>>(points, n, voxel_size, div_mode, bp, keys, bits, n_dev);
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_popc(bits, word_rank, max_words, bsums, d_n_out, s);
   if (rc) return rc;
-  box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank);
+  box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank, n_dev);
   DFB_LAUNCH_CHECK();
-  rc = segmented_mean(points, normals, nullptr, rank, n, 3, n, d_n_out, out_points, out_normals, a, s);
+  rc = segmented_mean(points, normals, nullptr, rank, n, 3, n, d_n_out, out_points, out_normals, a, s, n_dev);
   if (rc) return rc;
   box_finish_kernel<<<1, 1, 0, s>>>(bp, d_n_out);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
+}
+
+int dfb_point_box_filter(const float* points, const float* normals, int n, float voxel_size, int div_mode,
+                         float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  DFB_CHECK_ARG(n >= 0 && voxel_size > 0.f && d_n_out, "point_box_filter");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) { DFB_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), s)); return DFB_OK; }
+  DFB_CHECK_ARG(points && normals && out_points && out_normals && ws, "point_box_filter: null pointer");
+  Arena a(ws, ws_bytes);
+  return box_filter_impl(points, normals, n, nullptr, voxel_size, div_mode, out_points, out_normals, d_n_out, a, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused per-frame preprocessing (tracker.py:89-120): no host synchronisation, sizes stay on the device
+// ------------------------------------------------------------------------------------------------
+size_t dfb_preprocess_ws_bytes(int H, int W) {
+  const int n = (H / 2) * (W / 2) + 16;
+  Arena a(nullptr, 0);
+  a.take<float>((size_t)n * 4); a.take<int>(n + 1); a.take<int>(n + 1); a.take<int>(n / 2048 + 8); a.take<int>(8);
+  a.take<float>((size_t)n * 4); a.take<float>((size_t)n * 4); a.take<uint8_t>(n + 16); a.take<float>((size_t)n * 3);
+  a.take<float>((size_t)n * 3); a.take<float>((size_t)n * 3);
+  return a.off + dfb_pcproc_ws_bytes(n) + dfb_box_filter_ws_bytes(n) + 1024;
+}
+
+int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, float cx, float cy, int nb_points,
+                         float outlier_radius, int max_nn, float normal_radius, const float* h_cam_xyz, float box_voxel,
+                         int div_mode, float* out_points, float* out_normals, int32_t* d_n_out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  DFB_CHECK_ARG(depth && H >= 2 && W >= 2 && out_points && out_normals && d_n_out && ws && h_cam_xyz, "preprocess_frame");
+  DFB_CHECK_ARG(max_nn > 1 && max_nn <= 32 && nb_points > 0, "preprocess_frame: bad neighbour counts");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Hs = H / 2, Ws = W / 2, n = Hs * Ws;
+  Arena a(ws, ws_bytes);
+  float* pcA = a.take<float>((size_t)(n + 16) * 4);        // dense (uncompacted) unprojection
+  int* flag = a.take<int>(n + 17);
+  int* pos = a.take<int>(n + 17);
+  int* bsums = a.take<int>((n + 16) / 2048 + 8);
+  int* counts = a.take<int>(8);                             // [0] nA, [1] nB, [2] nC
+  float* pcB = a.take<float>((size_t)(n + 16) * 4);
+  float* pcC = a.take<float>((size_t)(n + 16) * 4);
+  uint8_t* mask = a.take<uint8_t>(n + 32);
+  float* nrmC = a.take<float>((size_t)(n + 16) * 3);
+  float* pD = a.take<float>((size_t)(n + 16) * 3);
+  float* nD = a.take<float>((size_t)(n + 16) * 3);
+  GridWs w;
+  grid_ws_layout(a, n + 16, &w);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  // P1: nearest x0.5 subsample (tracker.py:91-93) + unproject with halved intrinsics (:97-98) + validity flags
+  unproject_sub_kernel<<<div_up(n, 256), 256, 0, s>>>(depth, H, W, Hs, Ws, fx * 0.5f, fy * 0.5f, cx * 0.5f, cy * 0.5f, pcA, flag);
+  DFB_LAUNCH_CHECK();
+  int rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[0], s);
+  if (rc) return rc;
+  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB);
+  // P2: radius outlier filter
+  rc = build_grid(pcB, n, outlier_radius, w, s, &counts[0]);
+  if (rc) return rc;
+  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0]);
+  flag_from_mask_kernel<<<div_up(n, 256), 256, 0, s>>>(mask, n, &counts[0], flag);
+  DFB_LAUNCH_CHECK();
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[1], s);
+  if (rc) return rc;
+  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC);
+  // P3: normals
+  rc = build_grid(pcC, n, normal_radius, w, s, &counts[1]);
+  if (rc) return rc;
+  const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
+  if (max_nn <= 16)
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+  else
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+  flag_from_normals_kernel<<<div_up(n, 256), 256, 0, s>>>(nrmC, n, &counts[1], flag);
+  DFB_LAUNCH_CHECK();
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s);
+  if (rc) return rc;
+  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcC, nrmC, flag, pos, n, &counts[1], pD, nD);
+  DFB_LAUNCH_CHECK();
+  // P4: box filter
+  return box_filter_impl(pD, nD, n, &counts[2], box_voxel, div_mode, out_points, out_normals, d_n_out, a, s);
 }
 
 int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, int C, float* sum, int32_t* count,

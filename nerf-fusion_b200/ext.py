@@ -191,6 +191,29 @@ def point_box_filter(points, normals, voxel_size, div_mode=0):
     return out_p[:m], out_n[:m]
 
 
+def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, max_nn=16, normal_radius=0.1,
+                     cam_xyz=(0.0, 0.0, 0.0), box_voxel=0.02, div_mode=0):
+    """tracker.py:89-120 (geometry half) fused: full-resolution depth (H,W) with NaN = invalid and its intrinsics ->
+    (points (N,3), normals (N,3)) in camera space.  One device->host read (the row count)."""
+    _chk(depth, "depth", torch.float32)
+    H, W = depth.shape
+    dev = depth.device
+    n_max = (H // 2) * (W // 2)
+    out_p = torch.empty((n_max, 3), dtype=torch.float32, device=dev)
+    out_n = torch.empty((n_max, 3), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws = _WS.get(dev, lib.dfb_preprocess_ws_bytes(H, W))
+    with torch.cuda.device(dev):
+        check(lib.dfb_preprocess_frame(_p(depth), H, W, fx, fy, cx, cy, int(nb_points), float(outlier_radius), int(max_nn),
+                                       float(normal_radius), fptr(cam_xyz), float(box_voxel), int(div_mode), _p(out_p), _p(out_n),
+                                       _p(cnt), _p(ws), ws.numel(), _stream()))
+    m = int(cnt.item())
+    if m < 0:
+        raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
+    return out_p[:m], out_n[:m]
+
+
 # ----------------------------------------------------------------------------------------------- networks
 def encoder_forward(x, encoder_blob):
     _chk(x, "x", torch.float32)

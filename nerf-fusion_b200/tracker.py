@@ -69,6 +69,7 @@ class SDFTracker:
         # True: the whole Gauss-Newton solve of a frame is one C call (dfb_gauss_newton); False: the Python loop below
         # (same control flow, kept for A/B tests and as executable documentation of tracker.py:225-288)
         self.native_gn = True
+        self.fused_preprocess = True       # one C call for tracker.py:89-120 (False: the op-by-op path, same results)
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
         self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()
@@ -93,6 +94,9 @@ class SDFTracker:
     def preprocess_depth(self, depth_data, calib):
         """tracker.py:89-120 (geometry half): returns (points (N,3), normals (N,3)) in camera space."""
         pc_scale = self.sdf_args.subsample
+        if self.fused_preprocess and pc_scale == 0.5:
+            return ext.preprocess_frame(depth_data.contiguous(), calib.fx, calib.fy, calib.cx, calib.cy, 16, 0.05, 16, 0.1,
+                                        (0.0, 0.0, 0.0), 0.02, self.map.div_mode)
         pc_data = torch.nn.functional.interpolate(depth_data.unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
                                                   recompute_scale_factor=False).squeeze(0).squeeze(0).contiguous()
         pc_data = ext.unproject_depth(pc_data, calib.fx * pc_scale, calib.fy * pc_scale, calib.cx * pc_scale, calib.cy * pc_scale)

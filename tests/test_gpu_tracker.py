@@ -31,6 +31,28 @@ def _frame(T, i):
     return rgb.to(DEV).contiguous(), depth.to(DEV).contiguous()
 
 
+def test_fused_preprocess_equals_op_by_op(weights):
+    """dfb_preprocess_frame (no host sync) is bit-identical to the chain of drop-in ops + torch compactions."""
+    d = pkg()
+    m = make_map(weights)
+    trk = d.SDFTracker(m, ns(dict(TRACKING)))
+    seq = d.synth.SyntheticSequence(n_frames=2, device=DEV)
+    calib = d.FrameIntrinsic(*d.synth.ICL_CALIB)
+    for i in range(2):
+        depth, _ = seq.frame(i)
+        depth[(depth < 0.5) | (depth > 5.0)] = float("nan")
+        trk.fused_preprocess = True
+        pa, na = trk.preprocess_depth(depth, calib)
+        trk.fused_preprocess = False
+        pb, nb = trk.preprocess_depth(depth, calib)
+        assert pa.shape == pb.shape and pa.shape[0] > 20000
+        assert torch.equal(pa, pb) and torch.equal(na, nb)
+    # all-invalid frame
+    trk.fused_preprocess = True
+    pe, ne = trk.preprocess_depth(torch.full((480, 640), float("nan"), device=DEV), calib)
+    assert pe.shape[0] == 0 and ne.shape[0] == 0
+
+
 def test_preprocess_matches_golden(weights, T):
     d = pkg()
     m = make_map(weights)

@@ -123,6 +123,7 @@ struct Ctx {
   int row, part, grp; // row within the tile (= TMEM lane), column part owned by this thread, tile group
   uint32_t a_off, x_off;   // byte offsets of this group's activation / input tiles
   uint32_t mma_bar;   // shared address of the "MMA done" barrier
+  uint32_t wbar;      // shared address of the "weights landed" barrier (completes once)
   uint32_t phase;     // its parity
   uint32_t mask[4][CW / 32];   // ReLU masks of this thread's columns, per layer
 };
@@ -284,6 +285,7 @@ __device__ __forceinline__ void store_input(Ctx& c, const float* __restrict__ la
 // forward pass of the tile; returns pre-activation heads z (sdf) and u (std)
 __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  mbar_wait(c.wbar, 0);   // phase 0 completes once (bulk load of the network); later calls return immediately
   TC_LAYER((issue<4, 128, false, 128>(c, c.sa + c.x_off, c.sa + IMG_W0, false)));
   epi_fwd<128>(c, 0, DS_B0);
   TC_LAYER((issue<8, 128, false, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));
@@ -419,7 +421,7 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   tc_fence_after();
   c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
   c.tmem = c.tmem_base + 128u * c.grp;
-  mbar_wait(wbar, 0);
+  c.wbar = wbar;      // waited on in forward(): the weight load overlaps the first tile's map lookups and input staging
 }
 
 __device__ __forceinline__ void epilogue_free(Ctx& c) {

@@ -233,9 +233,10 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   float4 q = sorted[j];
   int3 c = cell_coord(g, q.x, q.y, q.z);
   float kd[K];
-  int ki[K];
+  int ki[K], ko[K];   // sorted-array position and ORIGINAL index (the tie-break that makes the result independent of the
+                      // atomics-defined order inside a grid cell; equal distances are common on a pixel lattice)
 #pragma unroll
-  for (int t = 0; t < K; ++t) { kd[t] = CUDART_INF_F; ki[t] = -1; }
+  for (int t = 0; t < K; ++t) { kd[t] = CUDART_INF_F; ki[t] = -1; ko[t] = 0x7fffffff; }
   const float r2 = radius * radius;
   for (int dx = -1; dx <= 1; ++dx) {
     int x = c.x + dx;
@@ -251,13 +252,15 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
         float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
         // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
         // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
-        if (d < r2 && d < kd[K - 1]) {
-          kd[K - 1] = d; ki[K - 1] = k;
+        const int o = __float_as_int(p.w);
+        if (d < r2 && (d < kd[K - 1] || (d == kd[K - 1] && o < ko[K - 1]))) {
+          kd[K - 1] = d; ki[K - 1] = k; ko[K - 1] = o;
 #pragma unroll
           for (int t = K - 1; t > 0; --t) {
-            if (kd[t] < kd[t - 1]) {
+            if (kd[t] < kd[t - 1] || (kd[t] == kd[t - 1] && ko[t] < ko[t - 1])) {
               float td = kd[t]; kd[t] = kd[t - 1]; kd[t - 1] = td;
               int ti = ki[t]; ki[t] = ki[t - 1]; ki[t - 1] = ti;
+              int to = ko[t]; ko[t] = ko[t - 1]; ko[t - 1] = to;
             }
           }
         }

@@ -36,6 +36,26 @@ WORKLOAD = "ICL-NUIM-shaped synthetic 640x480 RGB-D sequence, fusion-lr-kt.yaml,
 FLOP_FWD, FLOP_FWD_BWD = 98816, 182528            # per decoder query
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of this same command (profiles/); None when absent."""
+    import csv
+    f = ROOT / "profiles" / "r01_sdf_hg_tc_final_ncu_raw.csv"
+    if not f.exists():
+        return None
+    try:
+        rows = list(csv.reader(open(f)))
+        hdr, units, row = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            tot += float(row[i]) * mul
+        return tot
+    except Exception:
+        return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -212,7 +232,7 @@ def run_ours(args):
         "gpu_launches": int(res["launches"]),
         "roofline": {"bound": "tensor", "kernel": "sdf_hg_kernel (tcgen05 FP16 engine: fused decoder fwd+bwd+JtJ reduction)",
                      "achieved": round(ach, 3), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": round(ach / pk["bf16_sustained"], 5), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                     "frac": round(ach / pk["bf16_sustained"], 5), "traffic": ncu_traffic(), "peak_source": pk["src"] + " bf16 sustained",
                      "launches": res["hg_launches"], "avg_launch_us": round(1e6 * res["hg_time"] / max(res["hg_launches"], 1), 1)},
     }
     if world == 1:

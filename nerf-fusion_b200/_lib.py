@@ -52,6 +52,8 @@ SIGNATURES = {
     "dfb_encoder_blob_floats": (_SZ, []),
     "dfb_set_decoder_engine": (_I, [_I]),
     "dfb_get_decoder_engine": (_I, []),
+    "dfb_set_encoder_engine": (_I, [_I]),
+    "dfb_get_encoder_engine": (_I, []),
     "dfb_unproject_depth": (_I, [_P, _I, _I, _F, _F, _F, _F, _P, _P]),
     "dfb_pcproc_ws_bytes": (_SZ, [_I]),
     "dfb_remove_radius_outlier": (_I, [_P, _I, _I, _F, _P, _P, _SZ, _P]),

@@ -1,0 +1,237 @@
+// tcgen05 encoder engine (sm_100a): the per-sample encoder MLP 6 -> 32 -> 64 -> 256 -> 29 (network/di_encoder.py:26-30,
+// BatchNorm folded on the host) on the tensor cores, fused with the scatter-add into the per-voxel accumulators
+// (map.py:446-449, indexing.cu:59-71).  Same structure as decoder_tc.cu: FP16 weight images resident in shared memory
+// (one bulk-TMA load per CTA, 60 KB), FP32 accumulators in TMEM (256 columns per tile), 2 tiles in flight per CTA,
+// 8 warps per tile running the bias/ReLU/FP16 epilogues, inputs split hi + lo (the 6 inputs occupy one 16-column
+// k-step: columns 0..5 hi, 8..13 lo, weights duplicated).
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace dfb {
+namespace etc {
+using namespace tcp;
+
+constexpr int GROUPS = 2;
+constexpr int NPART = 2;
+constexpr int GT = T * NPART;
+constexpr int CTA_T = GT * GROUPS;
+// ---- blob (bytes) -----------------------------------------------------------------------------------------------------
+constexpr int IMG_W0 = 0;          // [ 32 rows x 64]: cols 0..5 = W0', cols 8..13 = W0' (lo halves)
+constexpr int IMG_W1 = 4096;       // [ 64 rows x 64]: cols 0..31
+constexpr int IMG_W2 = 12288;      // [256 rows x 64]
+constexpr int IMG_W3 = 45056;      // 4 blocks x [32 rows x 64]: rows 0..28 = W3
+constexpr int IMG_END = 61440;
+constexpr int ES_B0 = 0, ES_B1 = 32, ES_B2 = 96, ES_B3 = 352;   // FP32 biases (floats)
+constexpr int SMALL_BYTES = 2048;
+constexpr int BLOB_BYTES = IMG_END + SMALL_BYTES;   // 63488
+// ---- shared memory ------------------------------------------------------------------------------------------------------
+constexpr int SM_SMALL = IMG_END;
+constexpr int SM_A = BLOB_BYTES;                    // 62 * 1024: activation tile, 4 blocks x [128 x 64] fp16 per group
+constexpr int SM_TILE_BYTES = 65536;
+constexpr int SM_BAR = SM_A + GROUPS * SM_TILE_BYTES;
+constexpr int SM_TOTAL = SM_BAR + 64;
+constexpr int SM_ALLOC = SM_TOTAL + 1024;
+constexpr int TMEM_COLS = 256 * GROUPS;
+
+struct Sample {   // same 32-byte record as integrate.cu
+  int slot;
+  float rel[3];
+  float nrm[3];
+  int pad;
+};
+
+struct Ctx {
+  uint8_t* sm;
+  uint32_t sa, tmem, tmem_base, mma_bar, wbar, phase;
+  int row, part, grp;
+  uint32_t a_off;
+};
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
+
+template <int KSTEPS, int N, int B_ROWS>
+__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr) {
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
+  const uint64_t ad0 = smem_desc(a_addr, 16, 1024);
+  const uint64_t bd0 = smem_desc(b_addr, 16, 1024);
+#pragma unroll
+  for (int s = 0; s < KSTEPS; ++s) {
+    const uint64_t ad = ad0 + (uint64_t)(((s >> 2) * 16384 + (s & 3) * 32) >> 4);
+    const uint64_t bd = bd0 + (uint64_t)(((s >> 2) * (B_ROWS * 128) + (s & 3) * 32) >> 4);
+    mma_f16(c.tmem, ad, bd, idesc, s > 0 ? 1u : 0u);
+  }
+}
+
+#define ETC_LAYER(ISSUE_STMT)                         \
+  do {                                                \
+    fence_proxy_async();                              \
+    tc_fence_before();                                \
+    group_sync(c.grp);                                \
+    if (c.row == 0 && c.part == 0) {                  \
+      tc_fence_after();                               \
+      ISSUE_STMT;                                     \
+      mma_commit(c.mma_bar);                          \
+    }                                                 \
+    mbar_wait(c.mma_bar, c.phase);                    \
+    c.phase ^= 1u;                                    \
+    tc_fence_after();                                 \
+  } while (0)
+
+// hidden-layer epilogue: this thread's NCOLS / NPART columns: relu(D + b) -> FP16 activation tile
+template <int NCOLS>
+__device__ __forceinline__ void epi_hidden(Ctx& c, int bias_off) {
+  const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  constexpr int CW = NCOLS / NPART;
+  const uint32_t tbase = c.tmem + ((uint32_t)(c.row & ~31) << 16);
+  const int colb = CW * c.part;
+  if constexpr (CW == 16) {
+    float v[16];
+    tmem_ld16(tbase + colb, v);
+    const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + colb);
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 b = b4[i4];
+      v[4 * i4] = fmaxf(v[4 * i4] + b.x, 0.f); v[4 * i4 + 1] = fmaxf(v[4 * i4 + 1] + b.y, 0.f);
+      v[4 * i4 + 2] = fmaxf(v[4 * i4 + 2] + b.z, 0.f); v[4 * i4 + 3] = fmaxf(v[4 * i4 + 3] + b.w, 0.f);
+    }
+    store_cols<16>(c.sm + c.a_off, 16384, c.row, colb, v);
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < CW / 32; ++jj) {
+      const int col0 = colb + 32 * jj;
+      float v[32];
+      tmem_ld32(tbase + col0, v);
+      const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + col0);
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 b = b4[i4];
+        v[4 * i4] = fmaxf(v[4 * i4] + b.x, 0.f); v[4 * i4 + 1] = fmaxf(v[4 * i4 + 1] + b.y, 0.f);
+        v[4 * i4 + 2] = fmaxf(v[4 * i4 + 2] + b.z, 0.f); v[4 * i4 + 3] = fmaxf(v[4 * i4 + 3] + b.w, 0.f);
+      }
+      store_cols<32>(c.sm + c.a_off, 16384, c.row, col0, v);
+    }
+  }
+}
+
+extern __shared__ unsigned char etc_smem_raw[];
+
+__device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
+  const uint32_t raw = smem_u32(etc_smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  c.sm = etc_smem_raw + pad;
+  c.sa = raw + pad;
+  c.phase = 0;
+  c.grp = threadIdx.x / GT;
+  c.part = (threadIdx.x % GT) / T;
+  c.row = threadIdx.x % T;
+  c.a_off = SM_A + c.grp * SM_TILE_BYTES;
+  c.wbar = c.sa + SM_BAR;
+  const uint32_t slot = c.sa + SM_BAR + 48;
+  c.mma_bar = c.sa + SM_BAR + 8 + 8 * c.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(c.wbar, 1);
+    for (int g = 0; g < GROUPS; ++g) mbar_init(c.sa + SM_BAR + 8 + 8 * g, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_alloc(slot, TMEM_COLS);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(c.wbar, BLOB_BYTES);
+    const char* src = reinterpret_cast<const char*>(blob);
+    for (int off = 0; off < BLOB_BYTES; off += 15872) bulk_g2s(c.sa + off, src + off, 15872u, c.wbar);   // 4 x 15872 B
+  }
+  for (int i = threadIdx.x; i < GROUPS * SM_TILE_BYTES / 16; i += CTA_T) reinterpret_cast<uint4*>(c.sm + SM_A)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
+  c.tmem = c.tmem_base + 256u * c.grp;
+}
+
+// one tile: in[6] of this row already known to both threads of the row.  Leaves the 29 outputs (+bias) of columns
+// [16 part, 16 part + 16) in out16.
+__device__ __forceinline__ void encode_tile(Ctx& c, const float in[6], float out16[16]) {
+  const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
+  {
+    float h[8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float hi = __half2float(__float2half_rn(in[k]));
+      h[k] = c.part == 0 ? hi : in[k] - hi;
+    }
+    h[6] = 0.f; h[7] = 0.f;
+    store_cols<8>(c.sm + c.a_off, 16384, c.row, 8 * c.part, h);     // cols 0..7 hi, 8..15 lo
+  }
+  mbar_wait(c.wbar, 0);
+  ETC_LAYER((issue<1, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W0)));
+  epi_hidden<32>(c, ES_B0);
+  ETC_LAYER((issue<2, 64, 64>(c, c.sa + c.a_off, c.sa + IMG_W1)));
+  epi_hidden<64>(c, ES_B1);
+  ETC_LAYER((issue<4, 256, 256>(c, c.sa + c.a_off, c.sa + IMG_W2)));
+  epi_hidden<256>(c, ES_B2);
+  ETC_LAYER((issue<16, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W3)));
+  const uint32_t tbase = c.tmem + ((uint32_t)(c.row & ~31) << 16);
+  tmem_ld16(tbase + 16 * c.part, out16);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out16[i] += sm[ES_B3 + 16 * c.part + i];
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(CTA_T, 1) encoder_kernel(const Sample* __restrict__ samples, const float* __restrict__ x6, int m_host,
+                                                           const int* __restrict__ m_dev, const void* __restrict__ blob,
+                                                           float* __restrict__ out) {
+  Ctx c;
+  prologue(c, blob);
+  const int m = m_dev ? *m_dev : m_host;
+  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < m; tile += (long long)gridDim.x * GROUPS) {
+    const int i = (int)(tile * T) + c.row;
+    const bool valid = i < m;
+    float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int slot = 0;
+    if (valid) {
+      if (SCATTER) {
+        const Sample s = samples[i];
+        in[0] = s.rel[0]; in[1] = s.rel[1]; in[2] = s.rel[2]; in[3] = s.nrm[0]; in[4] = s.nrm[1]; in[5] = s.nrm[2];
+        slot = s.slot;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) in[k] = x6[(size_t)i * 6 + k];
+      }
+    }
+    float o[16];
+    encode_tile(c, in, o);
+    if (valid) {
+      float* dst = out + (size_t)(SCATTER ? slot : i) * DFB_LATENT_DIM + 16 * c.part;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        if (16 * c.part + l < DFB_LATENT_DIM) {
+          if (SCATTER) atomicAdd(dst + l, o[l]); else dst[l] = o[l];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
+}
+
+}  // namespace etc
+
+int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, float* acc, cudaStream_t s) {
+  DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
+  const int grid = (int)std::min<long long>(div_up(m_max, etc::T * etc::GROUPS), (long long)sm_count());
+  etc::encoder_kernel<true><<<grid, etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev, tc_blob, acc);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int tc_encoder_explicit(const float* x6, int m, const void* tc_blob, float* out, cudaStream_t s) {
+  DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
+  const int grid = (int)std::min<long long>(div_up(m, etc::T * etc::GROUPS), (long long)sm_count());
+  etc::encoder_kernel<false><<<grid, etc::CTA_T, etc::SM_ALLOC, s>>>(nullptr, x6, m, nullptr, tc_blob, out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // namespace dfb

@@ -120,4 +120,16 @@ def pack_encoder(W):
     p3 = np.zeros((256, 32), np.float32); p3[:, :29] = w3.T
     pb3 = np.zeros(32, np.float32); pb3[:29] = b3
     blob = np.concatenate([p0.reshape(-1), b0, w1.reshape(-1), b1, p2.reshape(-1), b2, p3.reshape(-1), pb3]).astype(np.float32)
-    return blob
+    return np.concatenate([blob, pack_encoder_tc(w0, b0, w1, b1, w2, b2, w3, b3).view(np.float32)])
+
+
+def pack_encoder_tc(w0, b0, w1, b1, w2, b2, w3, b3):
+    """FP16 SWIZZLE_128B images + FP32 biases for the tcgen05 encoder engine (csrc/encoder_tc.cu IMG_* / ES_*)."""
+    i0 = np.zeros((32, 64), np.float32); i0[:, 0:6] = w0; i0[:, 8:14] = w0          # hi | lo halves of the 6 inputs
+    i1 = np.zeros((64, 64), np.float32); i1[:, :32] = w1
+    i3 = np.zeros((32, 256), np.float32); i3[:29] = w3
+    img = np.concatenate([_swizzled_image(i0), _swizzled_image(i1), _swizzled_image(w2), _swizzled_image(i3)]).view(np.uint8)
+    assert img.size == 61440, img.size
+    sm = np.zeros(2048 // 4, np.float32)
+    sm[0:32] = b0; sm[32:96] = b1; sm[96:352] = b2; sm[352:381] = b3
+    return np.concatenate([img, sm.view(np.uint8)])

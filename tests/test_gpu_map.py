@@ -17,9 +17,9 @@ DEV = "cuda:0"
 def _fp32_engine():
     """Exact-parity tests use the FP32 CUDA-core decoder engine; tests/test_gpu_tc.py covers the tcgen05 engine."""
     lib = pkg()._lib.load()
-    lib.dfb_set_decoder_engine(0)
+    lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
     yield
-    lib.dfb_set_decoder_engine(1)
+    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(0)
 
 
 @pytest.fixture(scope="module")
@@ -48,7 +48,7 @@ def _check_state(m, G, tag):
 
 @pytest.fixture(scope="module")
 def gmap(weights, G):
-    pkg()._lib.load().dfb_set_decoder_engine(0)
+    pkg()._lib.load().dfb_set_decoder_engine(0); pkg()._lib.load().dfb_set_encoder_engine(0)
     m = make_map(weights)
     Pw, Nw = torch.from_numpy(G["Pw"]).to(DEV), torch.from_numpy(G["Nw"]).to(DEV)
     mask1 = m.integrate_keyframe(Pw, Nw)

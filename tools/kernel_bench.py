@@ -104,6 +104,14 @@ t = timeit(lambda: d.ext.gradient_xy(Iimg)); add("gradient_xy 640x480", t, nbyte
 G = d.ext.gradient_xy(Iimg)
 K = [481.2, 480.0, 319.5, 239.5]
 t = timeit(lambda: d.ext.rgb_hg(Iimg, depth, Iimg, depth, G, K, [1, 0, 0, 0, 1, 0, 0, 0, 1], [0.001, 0, 0], 0.0, 0.2, 0, 0.01, True)); add("rgb_hg 640x480 (residual+J+reduce)", t, nbytes=640 * 480 * 28, units=(640 * 480, "pixels"))
+# encoder engines on 2^20 samples
+xs = torch.cat([torch.rand(1 << 20, 3, device=DEV) - 0.5, torch.randn(1 << 20, 3, device=DEV)], 1).contiguous()
+eblob = torch.from_numpy(d.weights.pack_encoder(W)).to(DEV)
+for eng in (0, 1):
+    lib.dfb_set_encoder_engine(eng)
+    t = timeit(lambda: d.ext.encoder_forward(xs, eblob), iters=5)
+    add(f"encoder_forward 2^20 samples [{'tcgen05' if eng else 'fp32'}]", t, flop=(1 << 20) * 52096, units=(1 << 20, "samples"))
+lib.dfb_set_encoder_engine(0)
 # integrate (one keyframe, ~50k points) on a fresh default map
 P, Nn = d.ext.point_box_filter(p3, nr, 0.02)
 m2 = make_map(W)
@@ -111,8 +119,10 @@ R0 = torch.from_numpy(d.synth.quat_to_R(d.synth.FIRST_TQ[3:])).float().to(DEV); 
 Pw, Nw = (P @ R0.T + t0).contiguous(), (Nn @ R0.T).contiguous()
 def integ():
     mm = make_map(W); mm.integrate_keyframe(Pw, Nw)
-tb = timeit(lambda: make_map(W), iters=3, warm=1); ti = timeit(integ, iters=3, warm=1)
-add(f"integrate_keyframe ({Pw.shape[0]} pts, first keyframe incl. 1 host read)", ti - tb, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
+maps = [make_map(W) for _ in range(8)]
+it = iter(maps)
+ti = timeit(lambda: next(it).integrate_keyframe(Pw, Nw), iters=4, warm=2)
+add(f"integrate_keyframe ({Pw.shape[0]} pts, first keyframe of a fresh map, incl. 1 host read + buffer growth)", ti, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
 out = ROOT / "profiles" / "r01_kernel_table.md"
 keys = ["kernel", "time_us", "bound", "TFLOP/s", "GB/s", "frac", "units/s", "note"]
 with open(out, "w") as f:

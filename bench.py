@@ -211,6 +211,10 @@ def run_ours(args):
 
     res = run(e2e=False)
     res_e2e = run(e2e=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pk = peaks()

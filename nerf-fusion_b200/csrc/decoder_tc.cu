@@ -355,13 +355,6 @@ __device__ __forceinline__ void epilogue_free(Ctx& c) {
   if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
 }
 
-__device__ __forceinline__ void load_x(float* x32, const float* __restrict__ latent_row, const float rel[3], bool valid) {
-#pragma unroll
-  for (int k = 0; k < DFB_LATENT_DIM; ++k) x32[k] = valid ? __ldg(latent_row + k) : 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) x32[DFB_LATENT_DIM + k] = valid ? rel[k] : 0.f;
-}
-
 // The NPART threads of a row split the 29 Gauss-Newton sums (21 upper-triangle J J^T, 6 J r, energy, count): part p keeps
 // packed entries [8p, 8p+8) in acc[8].
 __device__ __forceinline__ void hg_accumulate_case(float* acc8, const float* J, float r, float w, bool with_J, int which) {

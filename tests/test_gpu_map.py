@@ -222,3 +222,44 @@ def test_integrate_edge_cases(weights):
     assert not mk.any()
     sdf, std, valid = m.get_sdf(outside)
     assert not valid.any() and sdf.numel() == 0
+
+
+@pytest.mark.parametrize("seed,voxel,bmin,bmax,prune", [
+    (0, 0.1, [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0], 16),
+    (1, 0.07, [-0.5, 0.0, -2.0], [1.3, 0.9, -0.6], 8),          # non-cubic grid, n_xyz not multiples of 32
+    (2, 0.25, [0.0, 0.0, 0.0], [3.0, 2.0, 1.0], 0),            # pruning disabled (unq_mask is None, map.py:373-374)
+    (3, 0.05, [-0.4, -0.4, -0.4], [0.4, 0.4, 0.4], 30),
+])
+def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, prune):
+    """Random surfaces in random grids (different voxel sizes, non-cubic extents, pruning thresholds, points on the
+    grid border): masks, voxel ids, slot order and counts bit-exact against the CPU oracle over three keyframes,
+    including voxels that cross the encoder_count_th = 600 threshold and stop being candidates."""
+    rng = np.random.RandomState(seed)
+    over = dict(bound_min=bmin, bound_max=bmax, voxel_size=voxel, prune_min_vox_obs=prune, encoder_count_th=120.0)
+    m = make_map(weights, **over)
+    from oracle.map_oracle import OracleMap
+    om = OracleMap(weights, bmin, bmax, voxel, 29, prune, 16.0, 120.0)
+    lo, hi = np.asarray(bmin, np.float32), np.asarray(bmax, np.float32)
+    for k in range(3):
+        n = 30000
+        uv = rng.rand(n, 2).astype(np.float32)
+        # a tilted, slightly curved sheet spanning the box + a dense clump touching the upper border
+        p = np.stack([uv[:, 0], uv[:, 1], 0.35 + 0.25 * uv[:, 0] + 0.1 * np.sin(5 * uv[:, 1] + k)], 1).astype(np.float32)
+        p = lo + p * (hi - lo) * np.float32(0.98) + np.float32(0.01) * (hi - lo)
+        clump = (hi - np.float32(1e-4)) - rng.rand(2000, 3).astype(np.float32) * np.float32(1.5 * voxel)
+        p = np.concatenate([p, clump]).astype(np.float32)
+        nr = rng.randn(p.shape[0], 3).astype(np.float32); nr /= np.linalg.norm(nr, axis=1, keepdims=True)
+        mk = m.integrate_keyframe(torch.from_numpy(p).to(DEV), torch.from_numpy(nr).to(DEV))
+        mo = om.integrate_keyframe(torch.from_numpy(p), torch.from_numpy(nr))
+        if prune > 0:
+            assert np.array_equal(mk.cpu().numpy(), mo.numpy())
+        else:
+            assert mk is None and mo is None
+        nocc = om.n_occupied
+        assert m.n_occupied == nocc and nocc > 0
+        assert np.array_equal(m.indexer.cpu().numpy(), om.indexer.numpy())
+        assert np.array_equal(m.latent_vecs_pos[:nocc].cpu().numpy(), om.latent_vecs_pos[:nocc].numpy())
+        assert np.array_equal(m.voxel_obs_count[:nocc].cpu().numpy(), om.voxel_obs_count[:nocc].numpy())
+        ref = om.latent_vecs[:nocc].numpy()
+        assert np.abs(m.latent_vecs[:nocc].cpu().numpy() - ref).max() <= 1e-3 * max(np.abs(ref).max(), 1e-6)
+    assert (om.voxel_obs_count[:nocc] >= 120.0).any()           # the candidate threshold was exercised

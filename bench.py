@@ -65,35 +65,66 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Uses NVML
+    in-process (a few microseconds per sample, every 20 ms); spawning nvidia-smi inside a timed region that lasts
+    ~100 ms stalls the launching thread behind the driver lock and showed up as 30 % run-to-run noise.  Falls back to
+    nvidia-smi when pynvml cannot open the device."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.stop = threading.Event()
         self.th = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.nvml = pynvml
+            self._sample_nvml()                       # first queries are slow (driver wake-up): keep them out of the timed region
+            self.rows.clear()
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        nv = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        self.rows.append([str(sm), str(mx)] + ["Active" if r & f else "Not Active" for f in flags])
 
     def _run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.02 if self.nvml is not None else 0.2)
 
     def __enter__(self):
+        if os.environ.get("BENCH_NO_CLOCKS") == "1":       # diagnostic only: measure the sampler's own interference
+            return self
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.th is not None:
+            self.th.join(timeout=6)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
@@ -101,7 +132,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -164,19 +195,23 @@ def run_ours(args):
             hg_events.append((a, b, float(trk._hg_host[43]), not no_grad))
             return out
         poses = []
+        trk.time_kernels = True
+        sampler = ClockSampler(local)                        # NVML is opened here, outside the timed region
         for i in range(Wm):
+            l2_flush.zero_()
             d, c = (t.to(dev, non_blocking=True) for t in host_frames[i]) if e2e else frames[i]
             poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))
         trk.compute_sdf_Hg = timed_sdf
-        trk.time_kernels = True
         trk.sdf_kernel_us = 0; trk.sdf_queries_J = 0; trk.sdf_queries_noJ = 0
         n_sdf_before = trk.n_sdf_evals
         dfb._lib.CALLS.clear()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wall0 = time.perf_counter()
+        trace = os.environ.get("BENCH_TRACE") == "1"
+        marks = []
         t0.record()
-        with ClockSampler(local) as cs:
+        with sampler as cs:
             for i in range(Wm, n_frames):
                 l2_flush.zero_()                                                  # cold L2 for every frame
                 if e2e:
@@ -184,8 +219,16 @@ def run_ours(args):
                 else:
                     d, c = frames[i]
                 poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))      # pose read back = D2H of H,g,e per GN term
+                if trace:
+                    ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append((ev, time.perf_counter()))
             t1.record()
             barrier()
+        if trace:
+            prev, prev_w = t0, wall0
+            per = []
+            for ev, w in marks:
+                per.append((round(prev.elapsed_time(ev), 2), round((w - prev_w) * 1e3, 2))); prev, prev_w = ev, w
+            print("per-frame (gpu ms, wall ms):", per, file=sys.stderr)
         wall = time.perf_counter() - wall0
         ms = t0.elapsed_time(t1)
         if world > 1:

@@ -54,8 +54,9 @@ size_t dfb_encoder_blob_floats(void);
  * Also settable with the environment variable DFB_DECODER_ENGINE before the first call. */
 int dfb_set_decoder_engine(int engine);
 int dfb_get_decoder_engine(void);
-/* Same switch for the encoder (dfb_integrate_commit, dfb_encoder_forward); env DFB_ENCODER_ENGINE.  Default 0 (FP32):
- * the FP16 tcgen05 encoder is 1.2e-3-relative accurate on latents, marginally outside the 1e-3 parity tolerance. */
+/* Same switch for the encoder (dfb_integrate_commit, dfb_encoder_forward); env DFB_ENCODER_ENGINE.  Default 1: the
+ * tcgen05 encoder splits weights and the inputs of layers 0..2 into FP16 hi + lo parts, which keeps latents within
+ * 1.8e-4 relative of the FP32 reference on the golden keyframe (tolerance 1e-3); 0 = FP32 CUDA cores (6e-7). */
 int dfb_set_encoder_engine(int engine);
 int dfb_get_encoder_engine(void);
 

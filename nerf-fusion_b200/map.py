@@ -82,11 +82,14 @@ class _GetSdfFn(torch.autograd.Function):
 
 class DenseIndexedMap:
     def __init__(self, model, args: argparse.Namespace, latent_dim: int, device: torch.device, enable_async: bool = False,
-                 optimization_device: torch.device = None, div_mode: int = DIV_IEEE):
+                 optimization_device: torch.device = None, div_mode: int = DIV_IEEE, reserve_voxels: int = 1 << 17):
         """model: an object with .decoder/.encoder torch modules (the reference's Networks), or a dict of checkpoint
         tensors with 'dec.'/'enc.' prefixed keys (weights.load_checkpoint / load_npz).
         div_mode: how x/voxel_size is rounded -- DIV_IEEE reproduces the reference on CPU (the parity oracle),
-        DIV_RECIP reproduces torch-CUDA's multiply-by-reciprocal."""
+        DIV_RECIP reproduces torch-CUDA's multiply-by-reciprocal.
+        reserve_voxels: rows of backing storage reserved up front (33 MB at the default 2^17).  The per-voxel tensors
+        in cold_vars are views of the first `capacity` rows, and capacity still doubles from 1 like map.py:263-285, so
+        growing the map is a re-slice -- no allocation or copy in the frame loop until the reservation is exceeded."""
         if enable_async:
             raise NotImplementedError("async optimisation/meshing is out of scope (run_async: false, SURVEY.md §8 I7)")
         if latent_dim != 29:
@@ -117,15 +120,12 @@ class DenseIndexedMap:
         self.cold_vars = {
             "n_occupied": 0,
             "indexer": torch.full((G,), -1, device=self.device, dtype=torch.long),
-            "latent_vecs": torch.zeros((1, latent_dim), dtype=torch.float32, device=self.device),
-            "latent_vecs_pos": torch.full((1,), -1, dtype=torch.long, device=self.device),
-            "voxel_obs_count": torch.zeros((1,), dtype=torch.float32, device=self.device),
-            "voxel_optimized": torch.zeros((1,), dtype=torch.bool, device=self.device),
         }
+        self._backing = None
+        self._reserve(max(1, int(reserve_voxels)), 1)
         # persistent zero-invariant scratch (include/difusion_b200.h, "Persistent per-map scratch")
         self._grid_count = torch.zeros((G,), dtype=torch.int32, device=self.device)
         self._grid_bits = torch.zeros(((G + 31) // 32 + 1,), dtype=torch.int32, device=self.device)
-        self._alloc_slot_scratch(1)
         self._n_new = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((4,), dtype=torch.int32, device=self.device)
         self._ws = None
@@ -155,14 +155,43 @@ class DenseIndexedMap:
             out["enc." + k] = v.detach().cpu()
         return out
 
-    def _alloc_slot_scratch(self, cap):
-        self._acc = torch.zeros((cap, self.latent_dim), dtype=torch.float32, device=self.device)
-        self._acc_n = torch.zeros((cap,), dtype=torch.int32, device=self.device)
-        self._touched = torch.zeros((cap,), dtype=torch.int32, device=self.device)
-        old = getattr(self, "_updated_flag", None)
-        self._updated_flag = torch.zeros((cap,), dtype=torch.uint8, device=self.device)
-        if old is not None:
-            self._updated_flag[:old.numel()] = old
+    _PER_VOXEL = ("latent_vecs", "latent_vecs_pos", "voxel_obs_count", "voxel_optimized")
+
+    def _reserve(self, rows, cap):
+        """(Re)allocate the backing storage with `rows` rows, keep the first min(old capacity, cap) rows of the current
+        per-voxel tensors, and point cold_vars at views of the first `cap` rows.  New rows are zero / -1 (map.py:263-285)."""
+        rows = max(rows, cap)
+        new = {
+            "latent_vecs": torch.zeros((rows, self.latent_dim), dtype=torch.float32, device=self.device),
+            "latent_vecs_pos": torch.full((rows,), -1, dtype=torch.long, device=self.device),
+            "voxel_obs_count": torch.zeros((rows,), dtype=torch.float32, device=self.device),
+            "voxel_optimized": torch.zeros((rows,), dtype=torch.bool, device=self.device),
+        }
+        flag = torch.zeros((rows,), dtype=torch.uint8, device=self.device)
+        for k in self._PER_VOXEL:
+            old = self.cold_vars.get(k)
+            if old is not None:
+                keep = min(old.size(0), cap)
+                new[k][:keep] = old[:keep].to(self.device)
+        old_flag = getattr(self, "_updated_flag", None)
+        if old_flag is not None:
+            keep = min(old_flag.numel(), rows)
+            flag[:keep] = old_flag[:keep]
+        self._backing = new
+        self._rows = rows
+        # per-slot scratch of the integrate kernels (zero-invariant between calls) and the meshing dirty flags
+        self._acc = torch.zeros((rows, self.latent_dim), dtype=torch.float32, device=self.device)
+        self._acc_n = torch.zeros((rows,), dtype=torch.int32, device=self.device)
+        self._touched = torch.zeros((rows,), dtype=torch.int32, device=self.device)
+        self._updated_flag = flag
+        self._view(cap)
+
+    def _view(self, cap):
+        for k in self._PER_VOXEL:
+            self.cold_vars[k] = self._backing[k][:cap]
+
+    def _is_backed(self):
+        return all(self.cold_vars[k].data_ptr() == self._backing[k].data_ptr() for k in self._PER_VOXEL)
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
@@ -178,29 +207,33 @@ class DenseIndexedMap:
     voxel_optimized = property(lambda s: s.cold_vars["voxel_optimized"], lambda s, v: s.cold_vars.__setitem__("voxel_optimized", v))
 
     def save(self, path):
+        """map.py:222-224.  The per-voxel views are cloned so the file holds `capacity` rows, not the reservation."""
+        cv = {k: (v.clone() if k in self._PER_VOXEL else v) for k, v in self.cold_vars.items()}
         with Path(path).open("wb") as f:
-            torch.save(self.cold_vars, f)
+            torch.save(cv, f)
 
     def load(self, path):
         with Path(path).open("rb") as f:
             cv = torch.load(f, map_location=self.device, weights_only=False)
         self.cold_vars = cv
-        self._alloc_slot_scratch(self.latent_vecs.size(0))
+        cap = self.latent_vecs.size(0)
+        self._updated_flag = None
+        self._reserve(max(self._rows, cap), cap)          # adopt the loaded tensors into the backing storage
+        self._updated_flag[:self.n_occupied] = 1          # every loaded voxel is dirty for the meshing cache
 
     def _inflate_latent_buffer(self, count: int):
         """map.py:263-285: capacity doubles until it holds n_occupied + count; new rows are zero / -1."""
         target = self.n_occupied + count
         cap = self.latent_vecs.size(0)
-        if cap < target:
-            new = cap
-            while new < target:
-                new *= 2
-            lv = torch.zeros((new, self.latent_dim), dtype=torch.float32, device=self.device); lv[:cap] = self.latent_vecs
-            lp = torch.full((new,), -1, dtype=torch.long, device=self.device); lp[:cap] = self.latent_vecs_pos
-            oc = torch.zeros((new,), dtype=torch.float32, device=self.device); oc[:cap] = self.voxel_obs_count
-            vo = torch.zeros((new,), dtype=torch.bool, device=self.device); vo[:cap] = self.voxel_optimized
-            self.latent_vecs, self.latent_vecs_pos, self.voxel_obs_count, self.voxel_optimized = lv, lp, oc, vo
-            self._alloc_slot_scratch(new)
+        new = cap
+        while new < target:
+            new *= 2
+        if not self._is_backed():                       # a caller replaced a cold_vars tensor: adopt it
+            self._reserve(max(self._rows, new), cap)
+        if new > self._rows:
+            self._reserve(max(new, 2 * self._rows), cap)
+        if new != cap:
+            self._view(new)
 
     def _linearize_id(self, xyz):
         return xyz[:, 2] + self.n_xyz[-1] * xyz[:, 1] + (self.n_xyz[-1] * self.n_xyz[-2]) * xyz[:, 0]

@@ -19,7 +19,7 @@ def _fp32_engine():
     lib = pkg()._lib.load()
     lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
     yield
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(0)
+    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
 
 
 @pytest.fixture(scope="module")
@@ -230,10 +230,13 @@ def test_integrate_edge_cases(weights):
     (2, 0.25, [0.0, 0.0, 0.0], [3.0, 2.0, 1.0], 0),            # pruning disabled (unq_mask is None, map.py:373-374)
     (3, 0.05, [-0.4, -0.4, -0.4], [0.4, 0.4, 0.4], 30),
 ])
-def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, prune):
+@pytest.mark.parametrize("enc_engine", [0, 1])
+def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, prune, enc_engine):
     """Random surfaces in random grids (different voxel sizes, non-cubic extents, pruning thresholds, points on the
     grid border): masks, voxel ids, slot order and counts bit-exact against the CPU oracle over three keyframes,
-    including voxels that cross the encoder_count_th = 600 threshold and stop being candidates."""
+    including voxels that cross the encoder_count_th = 600 threshold and stop being candidates.  Latents within the
+    1e-3 relative north-star tolerance under both encoder engines (FP32 CUDA cores / tcgen05)."""
+    pkg()._lib.load().dfb_set_encoder_engine(enc_engine)
     rng = np.random.RandomState(seed)
     over = dict(bound_min=bmin, bound_max=bmax, voxel_size=voxel, prune_min_vox_obs=prune, encoder_count_th=120.0)
     m = make_map(weights, **over)

@@ -16,7 +16,7 @@ def _fp32_engine():
     lib = pkg()._lib.load()
     lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
     yield
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(0)
+    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
 
 
 def _depth_frame(H=240, W=320, seed=0):

@@ -14,8 +14,9 @@ DEV = "cuda:0"
 @pytest.fixture()
 def engines():
     lib = pkg()._lib.load()
+    lib.dfb_set_encoder_engine(0)        # decoder-engine tests compare on identical (FP32-encoded) latents
     yield lib
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(0)
+    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
 
 
 def test_tc_decoder_forward_vs_oracle(weights, engines):
@@ -136,7 +137,7 @@ def test_tc_encoder_vs_oracle_and_golden(weights, engines):
         out[eng] = d.ext.encoder_forward(torch.from_numpy(x).to(DEV), blob).cpu().numpy()
     e0 = np.abs(out[0] - ref).max() / np.abs(ref).max(); e1 = np.abs(out[1] - ref).max() / np.abs(ref).max()
     print("encoder max err / max|ref|: fp32 engine %.2e, tcgen05 engine %.2e" % (e0, e1))
-    assert e0 < 1e-5 and e1 < 2e-3
+    assert e0 < 1e-5 and e1 < 1e-3      # measured 4.8e-4 (the FP16 rounding of the 256 inputs of the output layer)
     G = dict(np.load(GOLD / "map_golden.npz"))
     engines.dfb_set_encoder_engine(1)
     m = make_map(weights)
@@ -149,4 +150,4 @@ def test_tc_encoder_vs_oracle_and_golden(weights, engines):
     lat, refl = m.latent_vecs[:n].cpu().numpy(), G["k1_latent"]
     rel = np.abs(lat - refl).max() / np.abs(refl).max()
     print("integrate (tcgen05 encoder) latent max err / max|ref| = %.2e" % rel)
-    assert rel <= 2e-3          # FP16 weights: measured 1.15e-3; the FP32 encoder engine (default) gives 6e-7
+    assert rel <= 1e-3          # north-star tolerance; measured 1.8e-4 (the FP32 encoder engine gives 6e-7)

@@ -49,7 +49,7 @@ ids = torch.nonzero((rad > 48) & (rad < 56.5)).squeeze(-1)[:200000]
 V = ids.numel()
 m.cold_vars["latent_vecs"] = (torch.randn(V, 29, device=DEV) * 0.1); m.cold_vars["latent_vecs_pos"] = ids.clone()
 m.cold_vars["voxel_obs_count"] = torch.full((V,), 100.0, device=DEV); m.cold_vars["voxel_optimized"] = torch.zeros(V, dtype=torch.bool, device=DEV)
-m.indexer[ids] = torch.arange(V, device=DEV); m.cold_vars["n_occupied"] = V; m._alloc_slot_scratch(V)
+m.indexer[ids] = torch.arange(V, device=DEV); m.cold_vars["n_occupied"] = V; m._reserve(V, V)        # adopt the hand-built tensors
 print("synthetic map voxels:", V)
 trk = d.SDFTracker(m, dict(iter_config=[], sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
                            rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2)))
@@ -119,10 +119,18 @@ R0 = torch.from_numpy(d.synth.quat_to_R(d.synth.FIRST_TQ[3:])).float().to(DEV); 
 Pw, Nw = (P @ R0.T + t0).contiguous(), (Nn @ R0.T).contiguous()
 def integ():
     mm = make_map(W); mm.integrate_keyframe(Pw, Nw)
-maps = [make_map(W) for _ in range(8)]
-it = iter(maps)
-ti = timeit(lambda: next(it).integrate_keyframe(Pw, Nw), iters=4, warm=2)
-add(f"integrate_keyframe ({Pw.shape[0]} pts, first keyframe of a fresh map, incl. 1 host read + buffer growth)", ti, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
+for eng in (0, 1):
+    lib.dfb_set_encoder_engine(eng)
+    maps = [make_map(W) for _ in range(8)]
+    it = iter(maps)
+    ti = timeit(lambda: next(it).integrate_keyframe(Pw, Nw), iters=4, warm=2)
+    add(f"integrate_keyframe ({Pw.shape[0]} pts, first keyframe of a fresh map, incl. 1 host read + buffer growth) [{'tcgen05' if eng else 'fp32'} encoder]",
+        ti, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
+    mm = maps[0]
+    ti = timeit(lambda: mm.integrate_keyframe(Pw, Nw), iters=6, warm=2)
+    add(f"integrate_keyframe ({Pw.shape[0]} pts, repeated on the same map) [{'tcgen05' if eng else 'fp32'} encoder]",
+        ti, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
+lib.dfb_set_encoder_engine(1)
 out = ROOT / "profiles" / "r01_kernel_table.md"
 keys = ["kernel", "time_us", "bound", "TFLOP/s", "GB/s", "frac", "units/s", "note"]
 with open(out, "w") as f:

@@ -191,14 +191,20 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
                const float* decoder_blob, int robust, float robust_k, int compute_J, double* out44, void* stream);
 
 /* SDFTracker.gauss_newton (tracker.py:225-288) as ONE host call: for every group of the iteration config, up to n_iter
- * Gauss-Newton steps plus one evaluation-only pass, each evaluating the fused SDF term (dfb_sdf_hg) and/or the fused
- * photometric term (dfb_rgb_hg), reading 44 doubles back, solving the 6x6 system and updating the pose in float64;
- * a step whose energy rises is rolled back and ends its group (tracker.py:269-271).
- * Poses are 12 doubles: R row-major (9) then t (3).  h_delta_pose is in/out (initial guess -> result).
- * d_scratch80: device, 80 doubles.  h_pinned44: PINNED host memory, 44 doubles.
+ * Gauss-Newton steps plus one evaluation-only pass, each evaluating the fused SDF term and/or the fused photometric
+ * term.  The loop state lives on the device: a single-thread step kernel after the term kernels scales and adds the
+ * terms, solves the 6x6 system and updates the pose in float64, rolls a step back when its energy rises (which ends the
+ * group, tracker.py:269-271) and publishes the pose of the next evaluation, so nothing is read back between
+ * iterations; the host keeps one evaluation of look-ahead queued and only polls a 128-byte record per step.
+ * Poses are 12 doubles: R row-major (9) then t (3).  h_delta_pose is in/out (initial guess -> result; untouched on error).
+ * d_scratch: device, DFB_GN_SCRATCH_DOUBLES doubles.  h_pinned: PINNED (device-visible) host memory,
+ * DFB_GN_PINNED_DOUBLES doubles.
  * h_stats[8] = {last value of the iteration counter (tracker.py:281), #sdf evaluations, #rgb evaluations, status, ...}.
  * If h_stats[4] == 0x54494d45 on entry, the SDF-term launches are timed with CUDA events on `stream` and
- * h_stats[4..6] return {microseconds, valid queries with reverse pass, valid queries forward-only}. */
+ * h_stats[4..6] return {microseconds, valid queries with reverse pass, valid queries forward-only}.
+ * h_stats[7] = evaluations executed. */
+#define DFB_GN_SCRATCH_DOUBLES 160
+#define DFB_GN_PINNED_DOUBLES 64
 typedef struct {
   int32_t n_groups;              /* <= 8 */
   int32_t n_iter[8];             /* iter_config[i]["n"]                                  */
@@ -215,7 +221,7 @@ typedef struct {
 int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n,
                      const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
                      const float* decoder_blob, const dfb_rgb_level* h_levels, const double* h_intr,
-                     const double* h_last_pose, double* h_delta_pose, double* d_scratch80, double* h_pinned44,
+                     const double* h_last_pose, double* h_delta_pose, double* d_scratch, double* h_pinned,
                      int32_t* h_stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

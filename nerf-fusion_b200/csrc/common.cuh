@@ -158,4 +158,30 @@ __device__ __forceinline__ void hg_accumulate(float* acc, const float* J, float 
 // expands the packed 29 doubles (21 upper-tri, 6, 1, 1) into the public 44-double layout
 void launch_hg_expand(const double* packed, double* out44, cudaStream_t s);
 
+// ---- device-resident Gauss-Newton state (gauss_newton.cu) ------------------------------------------------------------
+// The term kernels of a Gauss-Newton evaluation read their pose from here and add their packed sums here; the
+// single-thread step kernel that follows them consumes the sums, solves, updates the pose and publishes the pose blocks
+// of the next evaluation, so the host never has to read H, g back between iterations.
+struct GnShared {
+  double sums[2][32];        // packed 29 sums of the SDF term [0] and the photometric term [1]; zero between evaluations
+  double delta[12], last_delta[12], last[12];   // poses: R row-major (9), t (3)
+  double last_energy;
+  double intr[4];            // fx, fy, cx, cy
+  float pose_sdf[36];        // PoseDev image of the next SDF evaluation (33 floats used)
+  float krk[12], kt[4];      // K R K^-1 (9 used), K t (3 used) of the next photometric evaluation
+  int done[8];               // group i finished (converged, rolled back or failed): its remaining launches return at once
+  int error;                 // 1 = singular normal equations
+};
+int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+                     const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
+                     cudaStream_t s);                                                                        // decoder.cu
+int launch_rgb_hg_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
+                     int compute_J, GnShared* gs, int gi, cudaStream_t s);                                   // photometric.cu
+struct GnRecord {            // written by the step kernel into pinned host memory, polled by the driver
+  int seq;                   // written last (after a system-wide fence)
+  int executed, broke, error;
+  double cnt[2];             // valid counts of the two terms
+  double delta[12];          // pose after this step
+};
+
 }  // namespace dfb

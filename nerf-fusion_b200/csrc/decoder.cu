@@ -92,7 +92,12 @@ __global__ void __launch_bounds__(DEC_T, 1) get_sdf_kernel(MapDev M, const float
 __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
                                                           const int64_t* __restrict__ indexer, const float* __restrict__ latents,
                                                           const float* __restrict__ obs_count, const float* __restrict__ blob,
-                                                          int robust, float robust_k, int with_J, double* __restrict__ packed) {
+                                                          int robust, float robust_k, int with_J, double* __restrict__ packed,
+                                                          const GnShared* __restrict__ gs, int gi) {
+  if (gs) {
+    if (gs->done[gi]) return;
+    P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
+  }
   DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
   decoder_load_small(S, blob);
   const int tid = threadIdx.x;
@@ -311,7 +316,7 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
   const PoseDev P = to_pose(h_pose);
   if (decoder_engine() == 1) {
     int rc = tc_sdf_hg(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), robust, robust_k,
-                       compute_J, packed, s);
+                       compute_J, packed, nullptr, 0, s);
     if (rc) return rc;
     launch_hg_expand(packed, out44, s);
     DFB_LAUNCH_CHECK();
@@ -320,7 +325,7 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
   int rc = set_dec_smem(sdf_hg_kernel);
   if (rc) return rc;
   sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count,
-                                                            decoder_blob, robust, robust_k, compute_J, packed);
+                                                            decoder_blob, robust, robust_k, compute_J, packed, nullptr, 0);
   launch_hg_expand(packed, out44, s);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
@@ -377,3 +382,23 @@ int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r,
 }
 
 }  // extern "C"
+
+// SDF term of one device-resident Gauss-Newton evaluation (gauss_newton.cu): pose and "group finished" flag come from
+// `gs`, the packed sums are added into gs->sums[0]; no memset, no expansion, no read back.
+namespace dfb {
+int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+                     const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
+                     cudaStream_t s) {
+  if (n == 0) return DFB_OK;
+  const PoseDev P = {};
+  if (decoder_engine() == 1)
+    return tc_sdf_hg(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), robust, robust_k, compute_J,
+                     gs->sums[0], gs, gi, s);
+  int rc = set_dec_smem(sdf_hg_kernel);
+  if (rc) return rc;
+  sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob,
+                                                            robust, robust_k, compute_J, gs->sums[0], gs, gi);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+}  // namespace dfb

@@ -43,6 +43,7 @@ struct PoseDev {
   float Rd[9], td[3];   // delta
   float Rl[9];          // last
 };
+static_assert(sizeof(PoseDev) == 33 * sizeof(float), "GnShared::pose_sdf holds a PoseDev image");
 
 static inline PoseDev to_pose(const float* h_pose) {
   PoseDev P;
@@ -88,7 +89,8 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
                const void* tc_blob, float* sdf, float* std_, uint8_t* valid, const float* g_sdf, const float* g_std,
                float* grad_xyz, cudaStream_t s);
 int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const int64_t* indexer, const float* latents,
-              const float* obs_count, const void* tc_blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s);
+              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, const GnShared* gs, int gi,
+              cudaStream_t s);
 int tc_cube_low(const float* latents, const int64_t* occ, int B, int r, float vsize, float a, const void* tc_blob, float* low_sdf,
                 float* low_std, cudaStream_t s);
 int tc_cube_refine(const float* latents, const int64_t* occ, int r, float vsize, float a, const void* tc_blob,

@@ -79,7 +79,7 @@ __device__ unsigned long long g_prof[256];
 __device__ int g_prof_n;
 #define PROF_MARK(c)                                                                         \
   do {                                                                                       \
-    if (blockIdx.x == 0 && (c).grp == 0 && (c).row == 0 && (c).half == 0) {                  \
+    if (blockIdx.x == 0 && (c).grp == 0 && (c).row == 0 && (c).part == 0) {                  \
       int k_ = g_prof_n; if (k_ < 256) { g_prof[k_] = clock64(); g_prof_n = k_ + 1; }        \
     }                                                                                        \
   } while (0)
@@ -464,7 +464,12 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
 __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
                                                       const int64_t* __restrict__ indexer, const float* __restrict__ latents,
                                                       const float* __restrict__ obs_count, const void* __restrict__ blob, int robust,
-                                                      float robust_k, int with_J, double* __restrict__ packed) {
+                                                      float robust_k, int with_J, double* __restrict__ packed,
+                                                      const GnShared* __restrict__ gs, int gi) {
+  if (gs) {                                      // device-resident Gauss-Newton: pose from the step kernel; a finished group returns at once
+    if (gs->done[gi]) return;
+    P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
+  }
   Ctx c;
   prologue(c, blob);
   float acc[HG_PER_THREAD];
@@ -597,11 +602,12 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
 }
 
 int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const int64_t* indexer, const float* latents,
-              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s) {
+              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, const GnShared* gs, int gi,
+              cudaStream_t s) {
   int rc = tc::prep(tc::sdf_hg_kernel);
   if (rc) return rc;
   tc::sdf_hg_kernel<<<tc::grid_for(n), tc::CTA_T, tc::SM_ALLOC, s>>>(M, P, obs, n, indexer, latents, obs_count, blob, robust, robust_k, with_J,
-                                                                   packed);
+                                                                   packed, gs, gi);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -1,11 +1,21 @@
-// Native Gauss-Newton driver: system/tracker.py:225-288 (gauss_newton) with the two fused terms, so one C call runs
-// the whole pose solve of a frame: per evaluation one kernel (+ a 352-byte read back), the 6x6 solve, the SE(3)
-// update and the accept / rollback logic in float64 on the host -- no Python, no torch ops, no extra syncs.
+// Native Gauss-Newton driver: system/tracker.py:225-288 (gauss_newton) with the two fused terms, device-resident.
+// One C call runs the whole pose solve of a frame.  An evaluation ("slot") is up to three launches on the caller's stream:
+//   [SDF term kernel] [photometric term kernel] [gn_step_kernel <<<1, 32>>>]
+// The term kernels read their pose from GnShared and add their packed sums there; the step kernel scales and sums the
+// terms, applies the accept / rollback rule, solves the 6x6 system (float64 LU, partial pivoting), composes the SE(3)
+// update, publishes the pose blocks of the next evaluation and writes a small record into pinned host memory.  The host
+// keeps ONE slot of look-ahead: slot k+1 is enqueued before the record of slot k is read, so the GPU never waits for
+// the host between evaluations; when slot k ends its group (energy rose -> rollback, tracker.py:269-271) the launches
+// of slot k+1 see done[group] and return immediately.
 // Pose algebra restated from utils/motion_util.py:205-228 (from_twist), :275-279 (inv, dot).
 #include <math.h>
 #include <string.h>
+#include <chrono>
+#include <vector>
 
 #include "common.cuh"
+
+#define HD __host__ __device__
 
 namespace {
 
@@ -13,14 +23,14 @@ struct Pose {   // x -> R x + t, float64
   double R[9], t[3];
 };
 
-void mat3_mul(const double* A, const double* B, double* C) {
+HD void mat3_mul(const double* A, const double* B, double* C) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
-void mat3_vec(const double* A, const double* v, double* o) {
+HD void mat3_vec(const double* A, const double* v, double* o) {
   for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
 }
-Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
+HD Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
   Pose c;
   mat3_mul(a.R, b.R, c.R);
   double rt[3];
@@ -31,7 +41,7 @@ Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
 
 // The reference stores rotations as unit quaternions (pyquaternion normalises on every rotation_matrix access), which
 // re-orthonormalises the pose each iteration; do the same round trip.
-void renormalise(double* R) {
+HD void renormalise(double* R) {
   double q[4];
   const double tr = R[0] + R[4] + R[8];
   if (tr > 0) {
@@ -54,7 +64,7 @@ void renormalise(double* R) {
   R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
 }
 
-Pose from_twist(const double* xi) {   // motion_util.py:205-228
+HD Pose from_twist(const double* xi) {   // motion_util.py:205-228
   Pose p;
   const double* rho = xi;
   const double* phi = xi + 3;
@@ -80,7 +90,7 @@ Pose from_twist(const double* xi) {   // motion_util.py:205-228
 }
 
 // np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular.
-bool solve6(const double* H, const double* g, double* x) {
+HD bool solve6(const double* H, const double* g, double* x) {
   double A[6][7];
   for (int i = 0; i < 6; ++i) {
     for (int j = 0; j < 6; ++j) A[i][j] = H[6 * i + j];
@@ -104,8 +114,108 @@ bool solve6(const double* H, const double* g, double* x) {
     x[r] = s / A[r][r];
   }
   for (int i = 0; i < 6; ++i)
-    if (!isfinite(x[i])) return false;
+    if (!(fabs(x[i]) <= 1.79769313486231570e308)) return false;   // non-finite
   return true;
+}
+
+
+// float images of the current pose for the two term kernels (same casts as the host-side wrappers: tracker.py:145-147, :201)
+__device__ void publish_pose(dfb::GnShared* gs) {
+  Pose last, delta;
+  for (int i = 0; i < 9; ++i) { last.R[i] = gs->last[i]; delta.R[i] = gs->delta[i]; }
+  for (int i = 0; i < 3; ++i) { last.t[i] = gs->last[9 + i]; delta.t[i] = gs->delta[9 + i]; }
+  const Pose total = compose(last, delta);
+  float* hp = gs->pose_sdf;                                   // PoseDev: Rt(9) tt(3) Rd(9) td(3) Rl(9)
+  for (int i = 0; i < 9; ++i) { hp[i] = (float)total.R[i]; hp[12 + i] = (float)delta.R[i]; hp[24 + i] = (float)last.R[i]; }
+  for (int i = 0; i < 3; ++i) { hp[9 + i] = (float)total.t[i]; hp[21 + i] = (float)delta.t[i]; }
+  const double fx = gs->intr[0], fy = gs->intr[1], cx = gs->intr[2], cy = gs->intr[3];
+  const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  const double Kinv[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
+  double KR[9], KRK[9], Kt[3];
+  mat3_mul(K, delta.R, KR); mat3_mul(KR, Kinv, KRK); mat3_vec(K, delta.t, Kt);
+  for (int i = 0; i < 9; ++i) gs->krk[i] = (float)KRK[i];
+  for (int i = 0; i < 3; ++i) gs->kt[i] = (float)Kt[i];
+}
+
+struct GnInit {
+  double last[12], delta[12], intr[4];
+};
+
+__global__ void gn_init_kernel(dfb::GnShared* gs, GnInit in) {
+  const int t = threadIdx.x;
+  if (t < 64) reinterpret_cast<double*>(gs->sums)[t] = 0.0;
+  if (t < 12) { gs->last[t] = in.last[t]; gs->delta[t] = in.delta[t]; gs->last_delta[t] = in.delta[t]; }
+  if (t < 4) gs->intr[t] = in.intr[t];
+  if (t < 8) gs->done[t] = 0;
+  if (t == 0) { gs->error = 0; gs->last_energy = CUDART_INF; }
+  __syncthreads();
+  if (t == 0) publish_pose(gs);
+}
+
+// One Gauss-Newton step (the body of the loop at tracker.py:240-281) for group gi, iteration `step` (step == n_it is the
+// evaluation-only pass, i_iter = -1).  Single thread, float64.
+__global__ void gn_step_kernel(dfb::GnShared* gs, dfb::GnRecord* ring, int seq, int gi, int step, int n_it, int use_sdf, int use_rgb,
+                               double rgb_weight) {
+  if (threadIdx.x != 0) return;
+  dfb::GnRecord* rec = ring + (seq & 3);
+  int executed = 0, broke = 0;
+  double cnt_out[2] = {0.0, 0.0};
+  if (!gs->done[gi]) {
+    executed = 1;
+    const bool no_grad = (step == n_it);
+    double H[36], g[6], energy = 0.0;
+    for (int i = 0; i < 36; ++i) H[i] = 0.0;
+    for (int i = 0; i < 6; ++i) g[i] = 0.0;
+    for (int term = 0; term < 2; ++term) {
+      if (!(term == 0 ? use_sdf : use_rgb)) continue;
+      double* p = gs->sums[term];
+      const double cnt = p[28];
+      cnt_out[term] = cnt;
+      const double scale = (term == 0 ? 1.0 : rgb_weight) / cnt;   // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
+      energy += p[27] * scale;
+      if (!no_grad) {
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b < 6; ++b) {
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            H[6 * a + b] += p[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)] * scale;
+          }
+        for (int i = 0; i < 6; ++i) g[i] += p[21 + i] * scale;
+      }
+      for (int i = 0; i < 29; ++i) p[i] = 0.0;                     // zero-invariant for the next evaluation
+    }
+    const double last_energy = step == 0 ? CUDART_INF : gs->last_energy;
+    if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
+      for (int i = 0; i < 12; ++i) gs->delta[i] = gs->last_delta[i];
+      gs->done[gi] = 1;
+      broke = 1;
+    } else {
+      for (int i = 0; i < 12; ++i) gs->last_delta[i] = gs->delta[i];
+      gs->last_energy = energy;
+      if (!no_grad) {
+        double xi[6];
+        if (!solve6(H, g, xi)) {
+          gs->error = 1;
+          for (int i = 0; i < 8; ++i) gs->done[i] = 1;
+        } else {
+          Pose d;
+          for (int i = 0; i < 9; ++i) d.R[i] = gs->delta[i];
+          for (int i = 0; i < 3; ++i) d.t[i] = gs->delta[9 + i];
+          Pose nd = compose(from_twist(xi), d);                     // tracker.py:277-278
+          renormalise(nd.R);
+          for (int i = 0; i < 9; ++i) gs->delta[i] = nd.R[i];
+          for (int i = 0; i < 3; ++i) gs->delta[9 + i] = nd.t[i];
+        }
+      } else {
+        gs->done[gi] = 1;                                           // the evaluation-only pass closes the group
+      }
+    }
+    publish_pose(gs);
+  }
+  rec->executed = executed; rec->broke = broke; rec->error = gs->error;
+  rec->cnt[0] = cnt_out[0]; rec->cnt[1] = cnt_out[1];
+  for (int i = 0; i < 12; ++i) rec->delta[i] = gs->delta[i];
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(&rec->seq) = seq;
 }
 
 }  // namespace
@@ -113,100 +223,146 @@ bool solve6(const double* H, const double* g, double* x) {
 extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n,
                                 const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
                                 const float* decoder_blob, const dfb_rgb_level* h_levels, const double* h_intr,
-                                const double* h_last_pose, double* h_delta_pose, double* d_scratch80, double* h_pinned44,
+                                const double* h_last_pose, double* h_delta_pose, double* d_scratch, double* h_pinned,
                                 int32_t* h_stats, void* stream) {
-  // optional kernel timing (CUDA events on the launching stream around every SDF term), reported through h_stats[4..7]:
-  // enabled when h_stats[4] == 0x54494d45 ('TIME') on entry
+  using dfb::GnRecord;
+  using dfb::GnShared;
+  static_assert(sizeof(GnShared) <= DFB_GN_SCRATCH_DOUBLES * sizeof(double), "d_scratch too small");
+  static_assert(4 * sizeof(GnRecord) <= DFB_GN_PINNED_DOUBLES * sizeof(double), "h_pinned too small");
+  // optional kernel timing (CUDA events on the launching stream around every SDF-term launch), reported through
+  // h_stats[4..6]: enabled when h_stats[4] == 0x54494d45 ('TIME') on entry
   const bool timing = h_stats && h_stats[4] == 0x54494d45;
-  static cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double sdf_ms = 0.0, sdf_q_j = 0.0, sdf_q_nj = 0.0;
-  if (timing && !ev0) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
-  DFB_CHECK_ARG(h_params && h_cfg && h_last_pose && h_delta_pose && d_scratch80 && h_pinned44 && h_stats, "gauss_newton");
+  DFB_CHECK_ARG(h_params && h_cfg && h_last_pose && h_delta_pose && d_scratch && h_pinned && h_stats, "gauss_newton");
   DFB_CHECK_ARG(h_cfg->n_groups >= 0 && h_cfg->n_groups <= 8, "gauss_newton: n_groups must be in [0, 8]");
   cudaStream_t s = (cudaStream_t)stream;
-  Pose last, delta, last_delta;
-  memcpy(last.R, h_last_pose, sizeof(double) * 9); memcpy(last.t, h_last_pose + 9, sizeof(double) * 3);
-  memcpy(delta.R, h_delta_pose, sizeof(double) * 9); memcpy(delta.t, h_delta_pose + 9, sizeof(double) * 3);
-  last_delta = delta;
-  int n_sdf = 0, n_rgb = 0, i_iter = 0;
-  const double fx = h_intr ? h_intr[0] : 1, fy = h_intr ? h_intr[1] : 1, cx = h_intr ? h_intr[2] : 0, cy = h_intr ? h_intr[3] : 0;
-  const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-  const double Kinv[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
+  GnShared* gs = reinterpret_cast<GnShared*>(d_scratch);
+  GnRecord* ring = nullptr;                                        // device view of the pinned ring
+  DFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ring), h_pinned, 0));
+  volatile GnRecord* hring = reinterpret_cast<volatile GnRecord*>(h_pinned);
+  for (int i = 0; i < 4; ++i) hring[i].seq = 0;
 
-  for (int gi = 0; gi < h_cfg->n_groups; ++gi) {
-    double last_energy = INFINITY;
+  static std::vector<cudaEvent_t> events;                           // pairs, grown on demand (timing only)
+  auto event = [&](size_t i) -> cudaEvent_t {
+    while (events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
+    return events[i];
+  };
+
+  GnInit init;
+  memcpy(init.last, h_last_pose, sizeof(double) * 12); memcpy(init.delta, h_delta_pose, sizeof(double) * 12);
+  for (int i = 0; i < 4; ++i) init.intr[i] = h_intr ? h_intr[i] : (i < 2 ? 1.0 : 0.0);
+  gn_init_kernel<<<1, 64, 0, s>>>(gs, init);
+  DFB_LAUNCH_CHECK();
+  const float intr4[4] = {(float)init.intr[0], (float)init.intr[1], (float)init.intr[2], (float)init.intr[3]};
+
+  static int seq_base = 0;                                          // records carry a process-unique, non-zero sequence number
+  struct Slot { int seq, gi, step, sdf_event; };
+  int n_sdf = 0, n_rgb = 0, n_steps = 0, i_iter = 0, n_events = 0, error = 0;
+  double sdf_ms = 0.0, sdf_q_j = 0.0, sdf_q_nj = 0.0;
+  double delta_out[12];
+  memcpy(delta_out, h_delta_pose, sizeof(delta_out));
+
+  auto enqueue = [&](int gi, int step, Slot& out) -> int {
     const int n_it = h_cfg->n_iter[gi];
-    for (int step = 0; step <= n_it; ++step) {          // n_it iterations + one evaluation-only pass (i_iter = -1)
-      i_iter = step < n_it ? step : -1;
-      const bool no_grad = (i_iter == -1);
-      double H[36], g[6], energy = 0.0;
-      memset(H, 0, sizeof(H)); memset(g, 0, sizeof(g));
-      for (int term = 0; term < 2; ++term) {
-        int rc = DFB_OK;
-        double scale_mul = 1.0;
-        if (term == 0) {
-          if (!h_cfg->use_sdf[gi]) continue;
-          const Pose total = compose(last, delta);
-          float hp[33];
-          for (int i = 0; i < 9; ++i) { hp[i] = (float)total.R[i]; hp[12 + i] = (float)delta.R[i]; hp[24 + i] = (float)last.R[i]; }
-          for (int i = 0; i < 3; ++i) { hp[9 + i] = (float)total.t[i]; hp[21 + i] = (float)delta.t[i]; }
-          if (timing) cudaEventRecord(ev0, s);
-          rc = dfb_sdf_hg(h_params, obs_xyz, n, hp, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
-                          h_cfg->sdf_robust_k, no_grad ? 0 : 1, d_scratch80, stream);
-          if (timing) cudaEventRecord(ev1, s);
-          ++n_sdf;
-        } else {
-          const int lvl = h_cfg->rgb_level[gi];
-          if (lvl < 0) continue;
-          DFB_CHECK_ARG(h_levels && h_intr && lvl < 3, "gauss_newton: rgb term needs pyramid levels and intrinsics");
-          double KR[9], KRK[9], Kt[3];
-          mat3_mul(K, delta.R, KR); mat3_mul(KR, Kinv, KRK); mat3_vec(K, delta.t, Kt);
-          float intr[4] = {(float)fx, (float)fy, (float)cx, (float)cy}, krk[9], kt[3];
-          for (int i = 0; i < 9; ++i) krk[i] = (float)KRK[i];
-          for (int i = 0; i < 3; ++i) kt[i] = (float)Kt[i];
-          const dfb_rgb_level& L = h_levels[lvl];
-          rc = dfb_rgb_hg(L.prev_I, L.prev_D, L.cur_I, L.cur_D, L.cur_G, L.H, L.W, intr, krk, kt, h_cfg->rgb_min_grad_scale,
-                          h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust, h_cfg->rgb_robust_k, no_grad ? 0 : 1, d_scratch80, stream);
-          scale_mul = h_cfg->rgb_weight;
-          ++n_rgb;
+    const bool no_grad = (step == n_it);
+    const int lvl = h_cfg->rgb_level[gi];
+    out.gi = gi; out.step = step; out.sdf_event = -1;
+    if (++seq_base == 0 || seq_base == INT32_MAX) seq_base = 1;
+    out.seq = seq_base;
+    if (h_cfg->use_sdf[gi]) {
+      if (timing) { out.sdf_event = n_events; cudaEventRecord(event(2 * n_events), s); }
+      int rc = dfb::launch_sdf_hg_gn(h_params, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
+                                     h_cfg->sdf_robust_k, no_grad ? 0 : 1, gs, gi, s);
+      if (rc) return rc;
+      if (timing) { cudaEventRecord(event(2 * n_events + 1), s); ++n_events; }
+    }
+    if (lvl >= 0) {
+      int rc = dfb::launch_rgb_hg_gn(&h_levels[lvl], intr4, h_cfg->rgb_min_grad_scale, h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust,
+                                     h_cfg->rgb_robust_k, no_grad ? 0 : 1, gs, gi, s);
+      if (rc) return rc;
+    }
+    gn_step_kernel<<<1, 32, 0, s>>>(gs, ring, out.seq, gi, step, n_it, h_cfg->use_sdf[gi] ? 1 : 0, lvl >= 0 ? 1 : 0, (double)h_cfg->rgb_weight);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  };
+  // wait for the record of a slot (spin on pinned memory; the stream is polled for errors now and then)
+  auto wait = [&](const Slot& sl, GnRecord& r) -> int {
+    volatile GnRecord* rec = hring + (sl.seq & 3);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0;; ++spin) {
+      if (rec->seq == sl.seq) { __atomic_thread_fence(__ATOMIC_ACQUIRE); break; }
+      if ((spin & 0xfff) == 0xfff) {
+        cudaError_t e = cudaStreamQuery(s);
+        if (e != cudaSuccess && e != cudaErrorNotReady) { dfb::set_error("gauss_newton: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
+        if (e == cudaSuccess && rec->seq != sl.seq) {               // stream drained without the record: cannot happen unless a launch failed
+          if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) { dfb::set_error("gauss_newton: step record never arrived"); return DFB_E_CUDA; }
         }
-        if (rc) return rc;
-        DFB_CUDA(cudaMemcpyAsync(h_pinned44, d_scratch80, sizeof(double) * 44, cudaMemcpyDeviceToHost, s));
-        DFB_CUDA(cudaStreamSynchronize(s));
-        const double cnt = h_pinned44[43];
-        if (timing && term == 0) {
-          float ms = 0.f;
-          cudaEventElapsedTime(&ms, ev0, ev1);
-          sdf_ms += ms;
-          (no_grad ? sdf_q_nj : sdf_q_j) += cnt;
-        }
-        const double scale = scale_mul / cnt;                 // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
-        energy += h_pinned44[42] * scale;
-        if (!no_grad) {
-          for (int i = 0; i < 36; ++i) H[i] += h_pinned44[i] * scale;
-          for (int i = 0; i < 6; ++i) g[i] += h_pinned44[36 + i] * scale;
-        }
-      }
-      if (energy > last_energy) {                             // tracker.py:269-271
-        delta = last_delta;
-        break;
-      }
-      last_delta = delta;
-      last_energy = energy;
-      if (!no_grad) {
-        double xi[6];
-        if (!solve6(H, g, xi)) { dfb::set_error("gauss_newton: singular normal equations"); h_stats[3] = 1; return DFB_E_INVALID; }
-        delta = compose(from_twist(xi), delta);               // tracker.py:277-278
-        renormalise(delta.R);
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) { dfb::set_error("gauss_newton: timed out waiting for the device"); return DFB_E_CUDA; }
       }
     }
+    r.executed = rec->executed; r.broke = rec->broke; r.error = rec->error;
+    r.cnt[0] = rec->cnt[0]; r.cnt[1] = rec->cnt[1];
+    for (int i = 0; i < 12; ++i) r.delta[i] = rec->delta[i];
+    return DFB_OK;
+  };
+  auto account = [&](const Slot& sl, const GnRecord& r) {
+    if (!r.executed) return;
+    const int n_it = h_cfg->n_iter[sl.gi];
+    const bool no_grad = (sl.step == n_it);
+    i_iter = no_grad ? -1 : sl.step;
+    ++n_steps;
+    if (h_cfg->use_sdf[sl.gi]) {
+      ++n_sdf;
+      if (timing && sl.sdf_event >= 0) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, event(2 * sl.sdf_event), event(2 * sl.sdf_event + 1));
+        sdf_ms += ms;
+        (no_grad ? sdf_q_nj : sdf_q_j) += r.cnt[0];
+      }
+    }
+    if (h_cfg->rgb_level[sl.gi] >= 0) ++n_rgb;
+    memcpy(delta_out, r.delta, sizeof(delta_out));
+    if (r.error) error = 1;
+  };
+
+  int rc = DFB_OK;
+  for (int gi = 0; gi < h_cfg->n_groups && rc == DFB_OK && !error; ++gi) {
+    const int n_it = h_cfg->n_iter[gi];
+    DFB_CHECK_ARG(n_it >= 0 && n_it < 100000, "gauss_newton: n_iter out of range");
+    if (h_cfg->rgb_level[gi] >= 0) DFB_CHECK_ARG(h_levels && h_intr && h_cfg->rgb_level[gi] < 3, "gauss_newton: rgb term needs pyramid levels and intrinsics");
+    Slot cur, next;
+    rc = enqueue(gi, 0, cur);
+    bool have_next = false;
+    for (int step = 0; rc == DFB_OK; ++step) {
+      have_next = false;
+      if (step + 1 <= n_it) {                                       // look-ahead: the next evaluation is queued before this one is read
+        rc = enqueue(gi, step + 1, next);
+        if (rc) break;
+        have_next = true;
+      }
+      GnRecord r;
+      rc = wait(cur, r);
+      if (rc) break;
+      account(cur, r);
+      const bool group_over = r.broke || r.error || step == n_it;
+      if (group_over) {
+        if (have_next) {                                            // already queued: it returns at once on the device; drain its record
+          rc = wait(next, r);
+          if (rc == DFB_OK) account(next, r);
+        }
+        break;
+      }
+      cur = next;
+    }
   }
-  memcpy(h_delta_pose, delta.R, sizeof(double) * 9); memcpy(h_delta_pose + 9, delta.t, sizeof(double) * 3);
+  if (rc) { cudaStreamSynchronize(s); return rc; }
+  if (error) { dfb::set_error("gauss_newton: singular normal equations"); h_stats[3] = 1; return DFB_E_INVALID; }
+  memcpy(h_delta_pose, delta_out, sizeof(double) * 12);
   h_stats[0] = i_iter; h_stats[1] = n_sdf; h_stats[2] = n_rgb; h_stats[3] = 0;
   if (timing) {
-    h_stats[4] = (int32_t)(sdf_ms * 1e3);        // microseconds spent in the SDF-term launches (memset + kernel + expand)
+    h_stats[4] = (int32_t)(sdf_ms * 1e3);        // microseconds spent in the SDF-term kernels
     h_stats[5] = (int32_t)sdf_q_j;               // valid queries evaluated with the reverse pass
     h_stats[6] = (int32_t)sdf_q_nj;              // valid queries evaluated forward-only
   }
+  h_stats[7] = n_steps;                          // evaluations executed (= step kernels that did work)
   return DFB_OK;
 }

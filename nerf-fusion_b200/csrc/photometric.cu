@@ -79,7 +79,15 @@ constexpr int HG_PIX_PER_THREAD = 4;
 
 __global__ void __launch_bounds__(HG_T) rgb_hg_kernel(const float* prev_I, const float* prev_D, const float* cur_I,
                                                       const float* cur_D, const float* dIdxy, int H, int W, RgbParams P,
-                                                      int robust, float robust_k, int with_J, double* out29) {
+                                                      int robust, float robust_k, int with_J, double* out29,
+                                                      const GnShared* __restrict__ gs, int gi) {
+  if (gs) {                                      // device-resident Gauss-Newton (gauss_newton.cu)
+    if (gs->done[gi]) return;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P.k[i] = gs->krk[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P.kt[i] = gs->kt[i];
+  }
   float acc[29];
 #pragma unroll
   for (int k = 0; k < 29; ++k) acc[k] = 0.f;
@@ -149,10 +157,24 @@ int dfb_rgb_hg(const float* prev_I, const float* prev_D, const float* cur_I, con
   double* packed = out44 + 44;
   DFB_CUDA(cudaMemsetAsync(out44, 0, sizeof(double) * 80, s));
   rgb_hg_kernel<<<div_up((long long)H * W, HG_T * HG_PIX_PER_THREAD), HG_T, 0, s>>>(
-      prev_I, prev_D, cur_I, cur_D, cur_dIdxy, H, W, P, robust, robust_k, compute_J, packed);
+      prev_I, prev_D, cur_I, cur_D, cur_dIdxy, H, W, P, robust, robust_k, compute_J, packed, nullptr, 0);
   launch_hg_expand(packed, out44, s);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
 
 }  // extern "C"
+
+// Photometric term of one device-resident Gauss-Newton evaluation: K R K^-1 and K t come from `gs`, sums go to gs->sums[1].
+namespace dfb {
+int launch_rgb_hg_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
+                     int compute_J, GnShared* gs, int gi, cudaStream_t s) {
+  RgbParams P = {};
+  P.fx = intr4[0]; P.fy = intr4[1]; P.cx = intr4[2]; P.cy = intr4[3];
+  P.min_grad_scale = min_grad_scale; P.max_depth_delta = max_depth_delta;
+  rgb_hg_kernel<<<div_up((long long)L->H * L->W, HG_T * HG_PIX_PER_THREAD), HG_T, 0, s>>>(
+      L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust, robust_k, compute_J, gs->sums[1], gs, gi);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+}  // namespace dfb

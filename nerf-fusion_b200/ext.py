@@ -192,9 +192,10 @@ def point_box_filter(points, normals, voxel_size, div_mode=0):
 
 
 def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, max_nn=16, normal_radius=0.1,
-                     cam_xyz=(0.0, 0.0, 0.0), box_voxel=0.02, div_mode=0):
+                     cam_xyz=(0.0, 0.0, 0.0), box_voxel=0.02, div_mode=0, sync=True):
     """tracker.py:89-120 (geometry half) fused: full-resolution depth (H,W) with NaN = invalid and its intrinsics ->
-    (points (N,3), normals (N,3)) in camera space.  One device->host read (the row count)."""
+    (points (N,3), normals (N,3)) in camera space.  One device->host read (the row count).
+    sync=False: no host read (CUDA-graph capturable); returns (points (n_max,3), normals (n_max,3), count i32[1])."""
     _chk(depth, "depth", torch.float32)
     H, W = depth.shape
     dev = depth.device
@@ -208,6 +209,8 @@ def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, m
         check(lib.dfb_preprocess_frame(_p(depth), H, W, fx, fy, cx, cy, int(nb_points), float(outlier_radius), int(max_nn),
                                        float(normal_radius), fptr(cam_xyz), float(box_voxel), int(div_mode), _p(out_p), _p(out_n),
                                        _p(cnt), _p(ws), ws.numel(), _stream()))
+    if not sync:
+        return out_p, out_n, cnt
     m = int(cnt.item())
     if m < 0:
         raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")

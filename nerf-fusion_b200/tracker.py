@@ -70,9 +70,15 @@ class SDFTracker:
         # (same control flow, kept for A/B tests and as executable documentation of tracker.py:225-288)
         self.native_gn = True
         self.fused_preprocess = True       # one C call for tracker.py:89-120 (False: the op-by-op path, same results)
+        # True: the per-frame front end (intensity, image pyramid, gradients, fused preprocessing: ~55 launches, no host
+        # decisions) is captured once per (image size, intrinsics) into a CUDA graph and replayed from static buffers
+        self.graph_frontend = True
+        self._fe_graphs = {}               # key -> dict(graph, static inputs/outputs)
+        self._fe_seen = {}                 # key -> eager calls so far (the first call warms kernels and workspaces up)
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
-        self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()
+        self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()       # DFB_GN_PINNED_DOUBLES
+        self._gn_dev = torch.zeros((160,), dtype=torch.float64, device=dev)          # DFB_GN_SCRATCH_DOUBLES
 
     # ------------------------------------------------------------------------------------------ preprocessing
     def _make_image_pyramid(self, intensity_img, depth_img):
@@ -111,12 +117,68 @@ class SDFTracker:
             pc_data = pc_data[ok, :3].contiguous()
         return point_box_filter(pc_data, normal_data, 0.02, self.map.div_mode)
 
+    def _frontend(self, rgb_data, depth_data, calib):
+        """Everything of tracker.py:75-120 that needs no host decision: intensity, pyramids, gradients, preprocessing.
+        Returns (Is, Ds, Gs, points (n_max,3), normals (n_max,3), count i32[1]); no host sync."""
+        cur_intensity = torch.mean(rgb_data, dim=-1)
+        Is, Ds, Gs = self._make_image_pyramid(cur_intensity, depth_data)
+        out_p, out_n, cnt = ext.preprocess_frame(Ds[0].contiguous(), calib.fx, calib.fy, calib.cx, calib.cy, 16, 0.05, 16, 0.1,
+                                                 (0.0, 0.0, 0.0), 0.02, self.map.div_mode, sync=False)
+        return Is, Ds, Gs, out_p, out_n, cnt
+
+    def _frontend_graphed(self, rgb_data, depth_data, calib):
+        """Replays the captured front end on copies of the inputs.  The first call per key runs eagerly (loads kernels,
+        sizes workspaces); later calls capture / replay.  Two graphs per key alternate (their outputs are static buffers,
+        and the pyramids of frame t are still read as `last_*` while frame t+1 is processed)."""
+        base = (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode)
+        seen = self._fe_seen.get(base, 0)
+        self._fe_seen[base] = seen + 1
+        if seen == 0:
+            return self._frontend(rgb_data, depth_data, calib)
+        key = base + (seen & 1,)
+        ent = self._fe_graphs.get(key)
+        if ent is None:
+            ent = dict(rgb=torch.empty_like(rgb_data), depth=torch.empty_like(depth_data))
+            ent["rgb"].copy_(rgb_data); ent["depth"].copy_(depth_data)
+            cur = torch.cuda.current_stream(self.map.device)
+            side = torch.cuda.Stream(self.map.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._frontend(ent["rgb"], ent["depth"], calib)
+            cur.wait_stream(side)
+            from . import _lib
+            before = dict(_lib.CALLS)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ent["out"] = self._frontend(ent["rgb"], ent["depth"], calib)
+            ent["graph"] = graph
+            ent["calls"] = {k: v - before.get(k, 0) for k, v in _lib.CALLS.items() if v != before.get(k, 0)}   # C calls inside one replay
+            self._fe_graphs[key] = ent
+        ent["rgb"].copy_(rgb_data); ent["depth"].copy_(depth_data)
+        ent["graph"].replay()
+        from . import _lib
+        for k, v in ent["calls"].items():                         # the replay launches the kernels of these calls again
+            _lib.CALLS[k] = _lib.CALLS.get(k, 0) + v
+        return ent["out"]
+
     def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False):
         """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid."""
-        cur_intensity = torch.mean(rgb_data, dim=-1)
-        cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
-        pc_data, normal_data = self.preprocess_depth(cur_depth[0], calib)
-        self.last_processed_pc = [pc_data, normal_data]
+        if self.fused_preprocess and self.sdf_args.subsample == 0.5:
+            graphed = self.graph_frontend
+            fe = self._frontend_graphed if graphed else self._frontend
+            with torch.cuda.device(self.map.device):
+                cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib)
+            m = int(cnt.item())                                   # the one host read of the front end
+            if m < 0:
+                raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
+            pc_data, normal_data = out_p[:m], out_n[:m]
+        else:
+            graphed = False
+            cur_intensity = torch.mean(rgb_data, dim=-1)
+            cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
+            pc_data, normal_data = self.preprocess_depth(cur_depth[0], calib)
+        # (graph outputs are static buffers reused two frames later: hand out copies)
+        self.last_processed_pc = [pc_data.clone(), normal_data.clone()] if graphed else [pc_data, normal_data]
         if for_pc:
             return self.last_processed_pc
         if set_pose is not None:
@@ -215,13 +277,13 @@ class SDFTracker:
         obs = obs_xyz.contiguous()
         with torch.cuda.device(m.device):
             check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0), _p(m.indexer), _p(m.latent_vecs),
-                                         _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._hg_dev),
+                                         _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._gn_dev),
                                          C.c_void_p(self._gn_pinned.data_ptr()), stats, _stream()))
         self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
         if self.time_kernels:
             self.sdf_kernel_us += stats[4]; self.sdf_queries_J += stats[5]; self.sdf_queries_noJ += stats[6]
-        _lib.CALLS["dfb_sdf_hg"] = _lib.CALLS.get("dfb_sdf_hg", 0) + stats[1]      # launches made inside the C driver
-        _lib.CALLS["dfb_rgb_hg"] = _lib.CALLS.get("dfb_rgb_hg", 0) + stats[2]
+        _lib.CALLS["gn_term"] = _lib.CALLS.get("gn_term", 0) + stats[1] + stats[2]      # launches made inside the C driver
+        _lib.CALLS["gn_step"] = _lib.CALLS.get("gn_step", 0) + stats[7]
         d = np.array(list(deltap), dtype=np.float64)
         new_delta = Isometry.from_matrix(d[:9].reshape(3, 3), d[9:12])
         if stats[0] >= 10:

@@ -21,10 +21,10 @@ trk.compute_sdf_Hg, trk.compute_rgb_Hg = sdf, rgb
 for i, (d, c) in enumerate(frames):
     if i == 5: T.clear()
     t0 = tic()
-    d = torch.where((d < 0.5) | (d > 5.0), torch.full_like(d, float('nan')), d)
-    I = torch.mean(c, dim=-1)
-    Is, Ds, Gs = trk._make_image_pyramid(I, d); add('pyramid', t0)
-    t0 = tic(); pc, nrm = trk.preprocess_depth(Ds[0], calib); add('preprocess', t0)
+    d = torch.where((d < 0.5) | (d > 5.0), torch.full_like(d, float('nan')), d); add('depth_cut', t0)
+    t0 = tic()
+    Is, Ds, Gs, out_p, out_n, cnt = trk._frontend_graphed(c.contiguous(), d.contiguous(), calib)
+    mcount = int(cnt.item()); pc, nrm = out_p[:mcount].clone(), out_n[:mcount].clone(); add('frontend (graph: pyramid + preprocess)', t0)
     trk.last_processed_pc = [pc, nrm]
     t0 = tic()
     if i == 0: pose = first

@@ -87,6 +87,18 @@ __device__ int g_prof_n;
 #define PROF_MARK(c) do {} while (0)
 #endif
 
+// Tile schedule of a persistent CTA: full rounds give every (CTA, group) slot one tile; the last, partial round hands its
+// tiles out one per CTA first (group 0 of every CTA, then group 1), so that a CTA whose sibling group has nothing left
+// runs its tile with the SM's issue slots and the tensor pipe to itself.  Returns -1 when the group is done.
+__device__ __forceinline__ long long tile_of(const Ctx& c, long long n, long long rnd) {
+  const long long tiles = (n + T - 1) / T, slots = (long long)gridDim.x * GROUPS;
+  const long long full = tiles / slots;
+  if (rnd < full) return rnd * slots + (long long)blockIdx.x * GROUPS + c.grp;
+  if (rnd > full) return -1;
+  const long long j = (long long)c.grp * gridDim.x + blockIdx.x;
+  return j < tiles - full * slots ? full * slots + j : -1;
+}
+
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
 
 // all threads of the group: make the tile writes visible to the tensor core, then thread 0 issues; everyone waits for completion
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restr
                                                         float* __restrict__ sdf, float* __restrict__ std_) {
   Ctx c;
   prologue(c, blob);
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const int i = (int)(tile * T) + c.row;
     {
       const float* xr = x + (size_t)(i < n ? i : 0) * 32;
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
                                                        const float* __restrict__ g_std, float* __restrict__ grad_xyz) {
   Ctx c;
   prologue(c, blob);
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const int i = (int)(tile * T) + c.row;
     bool valid = false;
     long long slot = 0;
@@ -471,12 +483,18 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
     P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
   }
   Ctx c;
+#ifdef DFB_TC_PROFILE
+  c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
+#endif
+  PROF_MARK(c);                                  // kernel start
   prologue(c, blob);
+  PROF_MARK(c);                                  // prologue done
   float acc[HG_PER_THREAD];
 #pragma unroll
   for (int k = 0; k < HG_PER_THREAD; ++k) acc[k] = 0.f;
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const int i = (int)(tile * T) + c.row;
+    PROF_MARK(c);                                // tile start
     bool valid = false;
     long long slot = 0;
     float rel[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
@@ -487,6 +505,7 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
       valid = map_lookup(M, pw[0], pw[1], pw[2], indexer, obs_count, slot, rel);
     }
     store_input(c, latents + (valid ? slot : 0) * DFB_LATENT_DIM, rel, valid);
+    PROF_MARK(c);                                // lookup + input staged
     float z, u;
     forward(c, z, u);
     const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
@@ -504,9 +523,12 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
       }
     }
     if (valid) hg_accumulate_part(acc, J, r, robust_w(r, robust, robust_k), with_J != 0, c.part);
+    PROF_MARK(c);                                // tile end
   }
   epilogue_free(c);
+  PROF_MARK(c);
   block_reduce_parts(acc, c.part, packed, reinterpret_cast<double*>(c.sm + SM_A));
+  PROF_MARK(c);                                  // kernel end
 }
 
 __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int B, int r,
@@ -515,7 +537,7 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restr
   Ctx c;
   prologue(c, blob);
   const long long r3 = (long long)r * r * r, n = (long long)B * r3;
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const long long i = tile * T + c.row;
     const bool valid = i < n;
     float rel[3] = {0.f, 0.f, 0.f};
@@ -542,7 +564,7 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_refine_kernel(const float* __re
   const int R = 2 * r;
   const long long R3 = (long long)R * R * R;
   const int n = *refine_count;
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < n; tile += (long long)gridDim.x * GROUPS) {
+  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const int t = (int)(tile * T) + c.row;
     const bool valid = t < n;
     float rel[3] = {0.f, 0.f, 0.f};
@@ -567,7 +589,7 @@ static int prep(K kernel) {
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
   return DFB_OK;
 }
-static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, T * GROUPS), (long long)sm_count()); }
+static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, T), (long long)sm_count()); }
 
 }  // namespace tc
 

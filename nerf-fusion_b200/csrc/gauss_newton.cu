@@ -15,69 +15,77 @@
 
 #include "common.cuh"
 
-#define HD __host__ __device__
-
 namespace {
 
+// All of this runs in one device thread (gn_step_kernel); loops have constant bounds and are unrolled so poses and the
+// 6x7 elimination tableau stay in registers (no local-memory traffic on the critical path between two evaluations).
 struct Pose {   // x -> R x + t, float64
   double R[9], t[3];
 };
 
-HD void mat3_mul(const double* A, const double* B, double* C) {
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
-HD void mat3_vec(const double* A, const double* v, double* o) {
+__device__ __forceinline__ void mat3_vec(const double* A, const double* v, double* o) {
+#pragma unroll
   for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
 }
-HD Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
+__device__ __forceinline__ Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
   Pose c;
   mat3_mul(a.R, b.R, c.R);
   double rt[3];
   mat3_vec(a.R, b.t, rt);
+#pragma unroll
   for (int i = 0; i < 3; ++i) c.t[i] = rt[i] + a.t[i];
   return c;
 }
 
 // The reference stores rotations as unit quaternions (pyquaternion normalises on every rotation_matrix access), which
 // re-orthonormalises the pose each iteration; do the same round trip.
-HD void renormalise(double* R) {
-  double q[4];
+__device__ __forceinline__ void renormalise(double* R) {
+  double q0, q1, q2, q3;
   const double tr = R[0] + R[4] + R[8];
   if (tr > 0) {
-    double s = sqrt(tr + 1.0) * 2;
-    q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s;
+    const double s = sqrt(tr + 1.0) * 2;
+    q0 = 0.25 * s; q1 = (R[7] - R[5]) / s; q2 = (R[2] - R[6]) / s; q3 = (R[3] - R[1]) / s;
   } else if (R[0] > R[4] && R[0] > R[8]) {
-    double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
-    q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s;
+    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+    q0 = (R[7] - R[5]) / s; q1 = 0.25 * s; q2 = (R[1] + R[3]) / s; q3 = (R[2] + R[6]) / s;
   } else if (R[4] > R[8]) {
-    double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
-    q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s;
+    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+    q0 = (R[2] - R[6]) / s; q1 = (R[1] + R[3]) / s; q2 = 0.25 * s; q3 = (R[5] + R[7]) / s;
   } else {
-    double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
-    q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s;
+    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+    q0 = (R[3] - R[1]) / s; q1 = (R[2] + R[6]) / s; q2 = (R[5] + R[7]) / s; q3 = 0.25 * s;
   }
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  const double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+  const double n = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+  const double w = q0 / n, x = q1 / n, y = q2 / n, z = q3 / n;
   R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
   R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
   R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
 }
 
-HD Pose from_twist(const double* xi) {   // motion_util.py:205-228
+__device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.py:205-228
   Pose p;
   const double* rho = xi;
   const double* phi = xi + 3;
   const double angle = sqrt(phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2]);
-  double Wd[9] = {0, -phi[2], phi[1], phi[2], 0, -phi[0], -phi[1], phi[0], 0};
+  const double Wd[9] = {0, -phi[2], phi[1], phi[2], 0, -phi[0], -phi[1], phi[0], 0};
   double J[9];
   if (fabs(angle) <= 1e-8) {   // np.isclose(angle, 0.)
+#pragma unroll
     for (int i = 0; i < 9; ++i) { p.R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Wd[i]; J[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Wd[i]; }
   } else {
     const double ax[3] = {phi[0] / angle, phi[1] / angle, phi[2] / angle};
-    const double s = sin(angle), c = cos(angle);
+    double s, c;
+    sincos(angle, &s, &c);
     const double Wa[9] = {0, -ax[2], ax[1], ax[2], 0, -ax[0], -ax[1], ax[0], 0};
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
       for (int j = 0; j < 3; ++j) {
         const double I = (i == j) ? 1.0 : 0.0, oo = ax[i] * ax[j];
         p.R[3 * i + j] = c * I + (1 - c) * oo + s * Wa[3 * i + j];
@@ -89,51 +97,74 @@ HD Pose from_twist(const double* xi) {   // motion_util.py:205-228
   return p;
 }
 
-// np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular.
-HD bool solve6(const double* H, const double* g, double* x) {
+// np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular / non-finite.
+__device__ __forceinline__ bool solve6(const double* H, const double* g, double* x) {
   double A[6][7];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
+#pragma unroll
     for (int j = 0; j < 6; ++j) A[i][j] = H[6 * i + j];
     A[i][6] = -g[i];
   }
+  bool ok = true;
+#pragma unroll
   for (int c = 0; c < 6; ++c) {
     int piv = c;
-    for (int r = c + 1; r < 6; ++r)
-      if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
-    if (!(fabs(A[piv][c]) > 0.0)) return false;
-    if (piv != c)
-      for (int j = 0; j < 7; ++j) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+    double best = fabs(A[c][c]);
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      const double v = fabs(A[r][c]);
+      if (v > best) { best = v; piv = r; }
+    }
+    if (!(best > 0.0)) ok = false;
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      if (piv == r) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { const double t = A[c][j]; A[c][j] = A[r][j]; A[r][j] = t; }
+      }
+    }
+#pragma unroll
     for (int r = c + 1; r < 6; ++r) {
       const double f = A[r][c] / A[c][c];
+#pragma unroll
       for (int j = c; j < 7; ++j) A[r][j] -= f * A[c][j];
     }
   }
+#pragma unroll
   for (int r = 5; r >= 0; --r) {
-    double s = A[r][6];
-    for (int j = r + 1; j < 6; ++j) s -= A[r][j] * x[j];
-    x[r] = s / A[r][r];
+    double sacc = A[r][6];
+#pragma unroll
+    for (int j = r + 1; j < 6; ++j) sacc -= A[r][j] * x[j];
+    x[r] = sacc / A[r][r];
   }
+#pragma unroll
   for (int i = 0; i < 6; ++i)
-    if (!(fabs(x[i]) <= 1.79769313486231570e308)) return false;   // non-finite
-  return true;
+    if (!(fabs(x[i]) <= 1.79769313486231570e308)) ok = false;   // non-finite
+  return ok;
 }
-
 
 // float images of the current pose for the two term kernels (same casts as the host-side wrappers: tracker.py:145-147, :201)
 __device__ void publish_pose(dfb::GnShared* gs) {
   Pose last, delta;
+  #pragma unroll
   for (int i = 0; i < 9; ++i) { last.R[i] = gs->last[i]; delta.R[i] = gs->delta[i]; }
+  #pragma unroll
   for (int i = 0; i < 3; ++i) { last.t[i] = gs->last[9 + i]; delta.t[i] = gs->delta[9 + i]; }
   const Pose total = compose(last, delta);
   float* hp = gs->pose_sdf;                                   // PoseDev: Rt(9) tt(3) Rd(9) td(3) Rl(9)
+  #pragma unroll
   for (int i = 0; i < 9; ++i) { hp[i] = (float)total.R[i]; hp[12 + i] = (float)delta.R[i]; hp[24 + i] = (float)last.R[i]; }
+  #pragma unroll
   for (int i = 0; i < 3; ++i) { hp[9 + i] = (float)total.t[i]; hp[21 + i] = (float)delta.t[i]; }
   const double fx = gs->intr[0], fy = gs->intr[1], cx = gs->intr[2], cy = gs->intr[3];
   const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
   const double Kinv[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
   double KR[9], KRK[9], Kt[3];
   mat3_mul(K, delta.R, KR); mat3_mul(KR, Kinv, KRK); mat3_vec(K, delta.t, Kt);
+  #pragma unroll
   for (int i = 0; i < 9; ++i) gs->krk[i] = (float)KRK[i];
+  #pragma unroll
   for (int i = 0; i < 3; ++i) gs->kt[i] = (float)Kt[i];
 }
 
@@ -164,8 +195,11 @@ __global__ void gn_step_kernel(dfb::GnShared* gs, dfb::GnRecord* ring, int seq, 
     executed = 1;
     const bool no_grad = (step == n_it);
     double H[36], g[6], energy = 0.0;
+    #pragma unroll
     for (int i = 0; i < 36; ++i) H[i] = 0.0;
+    #pragma unroll
     for (int i = 0; i < 6; ++i) g[i] = 0.0;
+    #pragma unroll
     for (int term = 0; term < 2; ++term) {
       if (!(term == 0 ? use_sdf : use_rgb)) continue;
       double* p = gs->sums[term];
@@ -174,35 +208,46 @@ __global__ void gn_step_kernel(dfb::GnShared* gs, dfb::GnRecord* ring, int seq, 
       const double scale = (term == 0 ? 1.0 : rgb_weight) / cnt;   // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
       energy += p[27] * scale;
       if (!no_grad) {
+        #pragma unroll
         for (int a = 0; a < 6; ++a)
+          #pragma unroll
           for (int b = 0; b < 6; ++b) {
             const int lo = a < b ? a : b, hi = a < b ? b : a;
             H[6 * a + b] += p[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)] * scale;
           }
+        #pragma unroll
         for (int i = 0; i < 6; ++i) g[i] += p[21 + i] * scale;
       }
+      #pragma unroll
       for (int i = 0; i < 29; ++i) p[i] = 0.0;                     // zero-invariant for the next evaluation
     }
     const double last_energy = step == 0 ? CUDART_INF : gs->last_energy;
     if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
+      #pragma unroll
       for (int i = 0; i < 12; ++i) gs->delta[i] = gs->last_delta[i];
       gs->done[gi] = 1;
       broke = 1;
     } else {
+      #pragma unroll
       for (int i = 0; i < 12; ++i) gs->last_delta[i] = gs->delta[i];
       gs->last_energy = energy;
       if (!no_grad) {
         double xi[6];
         if (!solve6(H, g, xi)) {
           gs->error = 1;
+          #pragma unroll
           for (int i = 0; i < 8; ++i) gs->done[i] = 1;
         } else {
           Pose d;
+          #pragma unroll
           for (int i = 0; i < 9; ++i) d.R[i] = gs->delta[i];
+          #pragma unroll
           for (int i = 0; i < 3; ++i) d.t[i] = gs->delta[9 + i];
           Pose nd = compose(from_twist(xi), d);                     // tracker.py:277-278
           renormalise(nd.R);
+          #pragma unroll
           for (int i = 0; i < 9; ++i) gs->delta[i] = nd.R[i];
+          #pragma unroll
           for (int i = 0; i < 3; ++i) gs->delta[9 + i] = nd.t[i];
         }
       } else {
@@ -213,6 +258,7 @@ __global__ void gn_step_kernel(dfb::GnShared* gs, dfb::GnRecord* ring, int seq, 
   }
   rec->executed = executed; rec->broke = broke; rec->error = gs->error;
   rec->cnt[0] = cnt_out[0]; rec->cnt[1] = cnt_out[1];
+  #pragma unroll
   for (int i = 0; i < 12; ++i) rec->delta[i] = gs->delta[i];
   __threadfence_system();
   *reinterpret_cast<volatile int*>(&rec->seq) = seq;

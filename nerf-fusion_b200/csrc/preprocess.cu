@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // uniform grid
 // ------------------------------------------------------------------------------------------------
-constexpr int GRID_CAP = 1 << 20;  // max cells
+constexpr int GRID_CAP = 1 << 22;        // max cells (workspace sizing)
+constexpr int GRID_CAP_COARSE = 1 << 20; // cell budget of the radius-count grid (cell = radius)
+constexpr int NORMAL_SUB = 4;            // the kNN grid of estimate_normals uses cells of radius / NORMAL_SUB
 
 struct GridParams {
   float ox, oy, oz, cell, inv_cell;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, 
   }
 }
 
-__global__ void grid_params_kernel(const unsigned* bbox, float radius, GridParams* gp) {
+__global__ void grid_params_kernel(const unsigned* bbox, float radius, int cap, GridParams* gp) {
   float lo[3], hi[3];
   for (int a = 0; a < 3; ++a) {
     lo[a] = ord2f(bbox[a]);
@@ -110,7 +112,7 @@ __global__ void grid_params_kernel(const unsigned* bbox, float radius, GridParam
     nx = (int)floorf((hi[0] - lo[0]) / cell) + 1;
     ny = (int)floorf((hi[1] - lo[1]) / cell) + 1;
     nz = (int)floorf((hi[2] - lo[2]) / cell) + 1;
-    if ((double)nx * ny * nz <= (double)GRID_CAP) break;
+    if ((double)nx * ny * nz <= (double)cap) break;
     cell *= 1.25f;
   }
   gp->ox = lo[0]; gp->oy = lo[1]; gp->oz = lo[2];
@@ -234,38 +236,55 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   int3 c = cell_coord(g, q.x, q.y, q.z);
   float kd[K];
   int ki[K], ko[K];   // sorted-array position and ORIGINAL index (the tie-break that makes the result independent of the
-                      // atomics-defined order inside a grid cell; equal distances are common on a pixel lattice)
+                      // atomics-defined order inside a grid cell and of the visiting order; equal distances are common
+                      // on a pixel lattice)
 #pragma unroll
   for (int t = 0; t < K; ++t) { kd[t] = CUDART_INF_F; ki[t] = -1; ko[t] = 0x7fffffff; }
   const float r2 = radius * radius;
-  for (int dx = -1; dx <= 1; ++dx) {
-    int x = c.x + dx;
-    if (x < 0 || x >= g.nx) continue;
-    for (int dy = -1; dy <= 1; ++dy) {
-      int y = c.y + dy;
-      if (y < 0 || y >= g.ny) continue;
-      int z0 = max(c.z - 1, 0), z1 = min(c.z + 1, g.nz - 1);
-      int row = (x * g.ny + y) * g.nz;
-      int b = cell_start[row + z0], e = cell_start[row + z1 + 1];
-      for (int k = b; k < e; ++k) {
-        float4 p = sorted[k];
-        float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-        // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
-        // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
-        const int o = __float_as_int(p.w);
-        if (d < r2 && (d < kd[K - 1] || (d == kd[K - 1] && o < ko[K - 1]))) {
-          kd[K - 1] = d; ki[K - 1] = k; ko[K - 1] = o;
+  auto scan = [&](int b, int e) {
+    for (int k = b; k < e; ++k) {
+      float4 p = sorted[k];
+      float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+      // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
+      // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
+      const int o = __float_as_int(p.w);
+      if (d < r2 && (d < kd[K - 1] || (d == kd[K - 1] && o < ko[K - 1]))) {
+        kd[K - 1] = d; ki[K - 1] = k; ko[K - 1] = o;
 #pragma unroll
-          for (int t = K - 1; t > 0; --t) {
-            if (kd[t] < kd[t - 1] || (kd[t] == kd[t - 1] && ko[t] < ko[t - 1])) {
-              float td = kd[t]; kd[t] = kd[t - 1]; kd[t - 1] = td;
-              int ti = ki[t]; ki[t] = ki[t - 1]; ki[t - 1] = ti;
-              int to = ko[t]; ko[t] = ko[t - 1]; ko[t - 1] = to;
-            }
+        for (int t = K - 1; t > 0; --t) {
+          if (kd[t] < kd[t - 1] || (kd[t] == kd[t - 1] && ko[t] < ko[t - 1])) {
+            float td = kd[t]; kd[t] = kd[t - 1]; kd[t - 1] = td;
+            int ti = ki[t]; ki[t] = ki[t - 1]; ki[t - 1] = ti;
+            int to = ko[t]; ko[t] = ko[t - 1]; ko[t - 1] = to;
           }
         }
       }
     }
+  };
+  // Expanding shells of cells around the query's cell (the grid is finer than the radius).  After the block [c-R, c+R]^3
+  // has been scanned every unvisited point is farther than R * cell from the query, so once the last entry that will
+  // be used is closer than that (with a margin for the rounding of cell_coord) the list is final: the exact K nearest.
+  const int Rmax = max(1, (int)ceilf(radius * g.inv_cell));
+  const int last = min(max_nn, K) - 1;
+  for (int R = 1; R <= Rmax; ++R) {
+    for (int dx = -R; dx <= R; ++dx) {
+      const int x = c.x + dx;
+      if (x < 0 || x >= g.nx) continue;
+      for (int dy = -R; dy <= R; ++dy) {
+        const int y = c.y + dy;
+        if (y < 0 || y >= g.ny) continue;
+        const int row = (x * g.ny + y) * g.nz;
+        if (R == 1 || dx == -R || dx == R || dy == -R || dy == R) {      // whole z-run (contiguous in memory)
+          const int z0 = max(c.z - R, 0), z1 = min(c.z + R, g.nz - 1);
+          scan(cell_start[row + z0], cell_start[row + z1 + 1]);
+        } else {                                                          // interior column: only the two new end cells
+          if (c.z - R >= 0) scan(cell_start[row + c.z - R], cell_start[row + c.z - R + 1]);
+          if (c.z + R < g.nz) scan(cell_start[row + c.z + R], cell_start[row + c.z + R + 1]);
+        }
+      }
+    }
+    const float reach = (float)R * g.cell * 0.9999f;
+    if (kd[last] < reach * reach) break;
   }
   int oi = __float_as_int(q.w);
   float3 mean = make_float3(0.f, 0.f, 0.f);
@@ -303,16 +322,17 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   normals[3 * oi + 2] = nrm.z;
 }
 
-static int build_grid(const float* pc4, int n, float radius, GridWs& w, cudaStream_t s, const int* n_dev = nullptr) {
+// cell: target cell edge (grown by 1.25x steps until the bounding box fits into `cap` cells)
+static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, cudaStream_t s, const int* n_dev = nullptr) {
   bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
-  grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, radius, w.gp);
-  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
+  grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp);
+  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (cap + 1), s));
   grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev);
   DFB_LAUNCH_CHECK();
-  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, GRID_CAP + 1, w.block_sums, nullptr, s);
+  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s);
   if (rc) return rc;
-  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (GRID_CAP + 1), s));
+  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (cap + 1), s));
   grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
@@ -556,7 +576,7 @@ int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radi
   GridWs w;
   grid_ws_layout(a, n, &w);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  int rc = build_grid(pc4, n, radius, w, s);
+  int rc = build_grid(pc4, n, radius, GRID_CAP_COARSE, w, s);
   if (rc) return rc;
   radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask, nullptr);
   DFB_LAUNCH_CHECK();
@@ -573,7 +593,7 @@ int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, cons
   GridWs w;
   grid_ws_layout(a, n, &w);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  int rc = build_grid(pc4, n, radius, w, s);
+  int rc = build_grid(pc4, n, radius / NORMAL_SUB, GRID_CAP, w, s);
   if (rc) return rc;
   float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16)
@@ -714,7 +734,7 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   if (rc) return rc;
   compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB);
   // P2: radius outlier filter
-  rc = build_grid(pcB, n, outlier_radius, w, s, &counts[0]);
+  rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0]);
   if (rc) return rc;
   radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0]);
   flag_from_mask_kernel<<<div_up(n, 256), 256, 0, s>>>(mask, n, &counts[0], flag);
@@ -723,7 +743,7 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   if (rc) return rc;
   compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC);
   // P3: normals
-  rc = build_grid(pcC, n, normal_radius, w, s, &counts[1]);
+  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1]);
   if (rc) return rc;
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16)

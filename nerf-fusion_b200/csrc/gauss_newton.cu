@@ -99,21 +99,21 @@ __device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.
 
 // np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular / non-finite.
 __device__ __forceinline__ bool solve6(const double* H, const double* g, double* x) {
-  double A[6][7];
+  double A[42];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) A[i][j] = H[6 * i + j];
-    A[i][6] = -g[i];
+    for (int j = 0; j < 6; ++j) A[7 * (i) + (j)] = H[6 * i + j];
+    A[7 * (i) + (6)] = -g[i];
   }
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     int piv = c;
-    double best = fabs(A[c][c]);
+    double best = fabs(A[7 * (c) + (c)]);
 #pragma unroll
     for (int r = c + 1; r < 6; ++r) {
-      const double v = fabs(A[r][c]);
+      const double v = fabs(A[7 * (r) + (c)]);
       if (v > best) { best = v; piv = r; }
     }
     if (!(best > 0.0)) ok = false;
@@ -121,22 +121,22 @@ __device__ __forceinline__ bool solve6(const double* H, const double* g, double*
     for (int r = c + 1; r < 6; ++r) {
       if (piv == r) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { const double t = A[c][j]; A[c][j] = A[r][j]; A[r][j] = t; }
+        for (int j = 0; j < 7; ++j) { const double t = A[7 * (c) + (j)]; A[7 * (c) + (j)] = A[7 * (r) + (j)]; A[7 * (r) + (j)] = t; }
       }
     }
 #pragma unroll
     for (int r = c + 1; r < 6; ++r) {
-      const double f = A[r][c] / A[c][c];
+      const double f = A[7 * (r) + (c)] / A[7 * (c) + (c)];
 #pragma unroll
-      for (int j = c; j < 7; ++j) A[r][j] -= f * A[c][j];
+      for (int j = c; j < 7; ++j) A[7 * (r) + (j)] -= f * A[7 * (c) + (j)];
     }
   }
 #pragma unroll
   for (int r = 5; r >= 0; --r) {
-    double sacc = A[r][6];
+    double sacc = A[7 * (r) + (6)];
 #pragma unroll
-    for (int j = r + 1; j < 6; ++j) sacc -= A[r][j] * x[j];
-    x[r] = sacc / A[r][r];
+    for (int j = r + 1; j < 6; ++j) sacc -= A[7 * (r) + (j)] * x[j];
+    x[r] = sacc / A[7 * (r) + (r)];
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -184,84 +184,102 @@ __global__ void gn_init_kernel(dfb::GnShared* gs, GnInit in) {
 }
 
 // One Gauss-Newton step (the body of the loop at tracker.py:240-281) for group gi, iteration `step` (step == n_it is the
-// evaluation-only pass, i_iter = -1).  Single thread, float64.
-__global__ void gn_step_kernel(dfb::GnShared* gs, dfb::GnRecord* ring, int seq, int gi, int step, int n_it, int use_sdf, int use_rgb,
-                               double rgb_weight) {
-  if (threadIdx.x != 0) return;
+// evaluation-only pass, i_iter = -1).  One warp: the state is staged through shared memory (one round of global loads
+// and one of stores, all lanes), the 36 + 6 normal-equation entries are scaled and summed lane-parallel, and lane 0 runs
+// the float64 solve and pose update out of registers.
+__global__ void __launch_bounds__(32) gn_step_kernel(dfb::GnShared* __restrict__ gs, dfb::GnRecord* __restrict__ ring, int seq, int gi, int step,
+                                                     int n_it, int use_sdf, int use_rgb, double rgb_weight) {
+  __shared__ dfb::GnShared sh;
+  __shared__ double Hs[36], gsv[6];
+  __shared__ int flags[2];                       // executed, broke
+  static_assert(sizeof(dfb::GnShared) % 8 == 0, "GnShared is copied as doubles");
+  constexpr int ND = sizeof(dfb::GnShared) / 8;
+  const int lane = threadIdx.x;
   dfb::GnRecord* rec = ring + (seq & 3);
-  int executed = 0, broke = 0;
-  double cnt_out[2] = {0.0, 0.0};
-  if (!gs->done[gi]) {
-    executed = 1;
-    const bool no_grad = (step == n_it);
-    double H[36], g[6], energy = 0.0;
-    #pragma unroll
-    for (int i = 0; i < 36; ++i) H[i] = 0.0;
-    #pragma unroll
-    for (int i = 0; i < 6; ++i) g[i] = 0.0;
-    #pragma unroll
-    for (int term = 0; term < 2; ++term) {
-      if (!(term == 0 ? use_sdf : use_rgb)) continue;
-      double* p = gs->sums[term];
-      const double cnt = p[28];
-      cnt_out[term] = cnt;
-      const double scale = (term == 0 ? 1.0 : rgb_weight) / cnt;   // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
-      energy += p[27] * scale;
-      if (!no_grad) {
-        #pragma unroll
-        for (int a = 0; a < 6; ++a)
-          #pragma unroll
-          for (int b = 0; b < 6; ++b) {
-            const int lo = a < b ? a : b, hi = a < b ? b : a;
-            H[6 * a + b] += p[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)] * scale;
-          }
-        #pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] += p[21 + i] * scale;
-      }
-      #pragma unroll
-      for (int i = 0; i < 29; ++i) p[i] = 0.0;                     // zero-invariant for the next evaluation
-    }
-    const double last_energy = step == 0 ? CUDART_INF : gs->last_energy;
-    if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
-      #pragma unroll
-      for (int i = 0; i < 12; ++i) gs->delta[i] = gs->last_delta[i];
-      gs->done[gi] = 1;
-      broke = 1;
-    } else {
-      #pragma unroll
-      for (int i = 0; i < 12; ++i) gs->last_delta[i] = gs->delta[i];
-      gs->last_energy = energy;
-      if (!no_grad) {
-        double xi[6];
-        if (!solve6(H, g, xi)) {
-          gs->error = 1;
-          #pragma unroll
-          for (int i = 0; i < 8; ++i) gs->done[i] = 1;
-        } else {
-          Pose d;
-          #pragma unroll
-          for (int i = 0; i < 9; ++i) d.R[i] = gs->delta[i];
-          #pragma unroll
-          for (int i = 0; i < 3; ++i) d.t[i] = gs->delta[9 + i];
-          Pose nd = compose(from_twist(xi), d);                     // tracker.py:277-278
-          renormalise(nd.R);
-          #pragma unroll
-          for (int i = 0; i < 9; ++i) gs->delta[i] = nd.R[i];
-          #pragma unroll
-          for (int i = 0; i < 3; ++i) gs->delta[9 + i] = nd.t[i];
-        }
-      } else {
-        gs->done[gi] = 1;                                           // the evaluation-only pass closes the group
-      }
-    }
-    publish_pose(gs);
+  {
+    const double* src = reinterpret_cast<const double*>(gs);
+    double* dst = reinterpret_cast<double*>(&sh);
+    for (int i = lane; i < ND; i += 32) dst[i] = src[i];
   }
-  rec->executed = executed; rec->broke = broke; rec->error = gs->error;
-  rec->cnt[0] = cnt_out[0]; rec->cnt[1] = cnt_out[1];
-  #pragma unroll
-  for (int i = 0; i < 12; ++i) rec->delta[i] = gs->delta[i];
-  __threadfence_system();
-  *reinterpret_cast<volatile int*>(&rec->seq) = seq;
+  __syncwarp();
+  const bool run = !sh.done[gi];
+  const bool no_grad = (step == n_it);
+  double cnt0 = 0.0, cnt1 = 0.0;
+  if (run) {
+    cnt0 = use_sdf ? sh.sums[0][28] : 0.0;
+    cnt1 = use_rgb ? sh.sums[1][28] : 0.0;
+    const double scale0 = 1.0 / cnt0, scale1 = rgb_weight / cnt1;   // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
+    if (!no_grad) {
+      for (int e = lane; e < 42; e += 32) {                          // SDF term first, then the photometric term (tracker.py:248-262)
+        int idx;
+        if (e < 36) {
+          const int a = e / 6, b = e % 6, lo = a < b ? a : b, hi = a < b ? b : a;
+          idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        } else {
+          idx = 21 + (e - 36);
+        }
+        double v = 0.0;
+        if (use_sdf) v += sh.sums[0][idx] * scale0;
+        if (use_rgb) v += sh.sums[1][idx] * scale1;
+        if (e < 36) Hs[e] = v; else gsv[e - 36] = v;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double energy = 0.0;
+      if (use_sdf) energy += sh.sums[0][27] * scale0;
+      if (use_rgb) energy += sh.sums[1][27] * scale1;
+      int broke = 0;
+      const double last_energy = step == 0 ? CUDART_INF : sh.last_energy;
+      if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sh.delta[i] = sh.last_delta[i];
+        sh.done[gi] = 1;
+        broke = 1;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sh.last_delta[i] = sh.delta[i];
+        sh.last_energy = energy;
+        if (!no_grad) {
+          double xi[6];
+          if (!solve6(Hs, gsv, xi)) {
+            sh.error = 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sh.done[i] = 1;
+          } else {
+            Pose d;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) d.R[i] = sh.delta[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) d.t[i] = sh.delta[9 + i];
+            Pose nd = compose(from_twist(xi), d);                     // tracker.py:277-278
+            renormalise(nd.R);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sh.delta[i] = nd.R[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sh.delta[9 + i] = nd.t[i];
+          }
+        } else {
+          sh.done[gi] = 1;                                            // the evaluation-only pass closes the group
+        }
+      }
+      publish_pose(&sh);
+      flags[1] = broke;
+    }
+    __syncwarp();
+    for (int i = lane; i < 64; i += 32) reinterpret_cast<double*>(sh.sums)[i] = 0.0;   // zero-invariant for the next evaluation
+    __syncwarp();
+    double* dst = reinterpret_cast<double*>(gs);
+    const double* src = reinterpret_cast<const double*>(&sh);
+    for (int i = lane; i < ND; i += 32) dst[i] = src[i];
+  }
+  // record for the host (pinned memory): payload from all lanes, then a system-wide fence, then the sequence number
+  if (lane < 12) rec->delta[lane] = sh.delta[lane];
+  if (lane == 12) { rec->executed = run ? 1 : 0; rec->broke = run ? flags[1] : 0; rec->error = sh.error; }
+  if (lane == 13) { rec->cnt[0] = cnt0; rec->cnt[1] = cnt1; }
+  __threadfence_system();                        // every lane: its payload stores are visible system-wide ...
+  __syncwarp();                                  // ... before lane 0 publishes the sequence number
+  if (lane == 0) *reinterpret_cast<volatile int*>(&rec->seq) = seq;
 }
 
 }  // namespace

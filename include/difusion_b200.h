@@ -202,7 +202,7 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
  * h_stats[8] = {last value of the iteration counter (tracker.py:281), #sdf evaluations, #rgb evaluations, status, ...}.
  * If h_stats[4] == 0x54494d45 on entry, the SDF-term launches are timed with CUDA events on `stream` and
  * h_stats[4..6] return {microseconds, valid queries with reverse pass, valid queries forward-only}.
- * h_stats[7] = evaluations executed. */
+ * h_stats[7] = kernels launched by the call. */
 #define DFB_GN_SCRATCH_DOUBLES 160
 #define DFB_GN_PINNED_DOUBLES 64
 typedef struct {

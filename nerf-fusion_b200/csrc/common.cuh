@@ -171,12 +171,24 @@ struct GnShared {
   float krk[12], kt[4];      // K R K^-1 (9 used), K t (3 used) of the next photometric evaluation
   int done[8];               // group i finished (converged, rolled back or failed): its remaining launches return at once
   int error;                 // 1 = singular normal equations
+  int ticket;                // blocks of the evaluation's last term kernel that have finished (last-block-done step)
+  int rgb_cursor;            // next chunk of photometric pixels (work stealing inside the fused evaluation kernel)
+  int pad_;
 };
 int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
                      const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
                      cudaStream_t s);                                                                        // decoder.cu
 int launch_rgb_hg_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
                      int compute_J, GnShared* gs, int gi, cudaStream_t s);                                   // photometric.cu
+namespace gn { struct StepArgs; }
+// fused evaluation (tcgen05 engine): SDF term + optional photometric term (L may be null) + step, one launch      // decoder.cu / decoder_tc.cu
+int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+                      const float* voxel_obs_count, const float* decoder_blob, int sdf_robust, float sdf_robust_k, int compute_J,
+                      const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int rgb_robust,
+                      float rgb_robust_k, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s);
+// photometric term + step, one launch                                                                                // photometric.cu
+int launch_rgb_step_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
+                       int compute_J, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s);
 struct GnRecord {            // written by the step kernel into pinned host memory, polled by the driver
   int seq;                   // written last (after a system-wide fence)
   int executed, broke, error;

@@ -7,6 +7,8 @@
 
 #include "decoder_common.cuh"
 #include "decoder_simt.cuh"
+#include "photometric.cuh"
+#include "gn_step.cuh"
 
 namespace dfb {
 
@@ -316,7 +318,7 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
   const PoseDev P = to_pose(h_pose);
   if (decoder_engine() == 1) {
     int rc = tc_sdf_hg(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), robust, robust_k,
-                       compute_J, packed, nullptr, 0, s);
+                       compute_J, packed, s);
     if (rc) return rc;
     launch_hg_expand(packed, out44, s);
     DFB_LAUNCH_CHECK();
@@ -383,17 +385,30 @@ int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r,
 
 }  // extern "C"
 
-// SDF term of one device-resident Gauss-Newton evaluation (gauss_newton.cu): pose and "group finished" flag come from
-// `gs`, the packed sums are added into gs->sums[0]; no memset, no expansion, no read back.
+// Gauss-Newton evaluations launched by gauss_newton.cu.
 namespace dfb {
+// tcgen05 engine: SDF term + optional photometric term + step in one launch (decoder_tc.cu gn_eval_kernel)
+int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+                      const float* voxel_obs_count, const float* decoder_blob, int sdf_robust, float sdf_robust_k, int compute_J,
+                      const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int rgb_robust,
+                      float rgb_robust_k, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s) {
+  RgbDev R = {};
+  if (L) {
+    R.prev_I = L->prev_I; R.prev_D = L->prev_D; R.cur_I = L->cur_I; R.cur_D = L->cur_D; R.cur_G = L->cur_G; R.H = L->H; R.W = L->W;
+    R.P.fx = intr4[0]; R.P.fy = intr4[1]; R.P.cx = intr4[2]; R.P.cy = intr4[3];
+    R.P.min_grad_scale = min_grad_scale; R.P.max_depth_delta = max_depth_delta;
+    R.robust = rgb_robust; R.robust_k = rgb_robust_k; R.on = 1;
+  }
+  return tc_gn_eval(to_dev(h_params), obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), sdf_robust, sdf_robust_k,
+                    compute_J, R, gs, gi, *sa, s);
+}
+
+// FP32 CUDA-core engine: the SDF term alone (pose and "group finished" flag from `gs`, sums into gs->sums[0])
 int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
                      const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
                      cudaStream_t s) {
   if (n == 0) return DFB_OK;
   const PoseDev P = {};
-  if (decoder_engine() == 1)
-    return tc_sdf_hg(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), robust, robust_k, compute_J,
-                     gs->sums[0], gs, gi, s);
   int rc = set_dec_smem(sdf_hg_kernel);
   if (rc) return rc;
   sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob,

@@ -89,8 +89,12 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
                const void* tc_blob, float* sdf, float* std_, uint8_t* valid, const float* g_sdf, const float* g_std,
                float* grad_xyz, cudaStream_t s);
 int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const int64_t* indexer, const float* latents,
-              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, const GnShared* gs, int gi,
-              cudaStream_t s);
+              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s);
+struct RgbDev;
+namespace gn { struct StepArgs; }
+int tc_gn_eval(const MapDev& M, const float* obs, int n, const int64_t* indexer, const float* latents, const float* obs_count,
+               const void* blob, int robust, float robust_k, int with_J, const RgbDev& R, GnShared* gs, int gi, const gn::StepArgs& sa,
+               cudaStream_t s);
 int tc_cube_low(const float* latents, const int64_t* occ, int B, int r, float vsize, float a, const void* tc_blob, float* low_sdf,
                 float* low_std, cudaStream_t s);
 int tc_cube_refine(const float* latents, const int64_t* occ, int r, float vsize, float a, const void* tc_blob,

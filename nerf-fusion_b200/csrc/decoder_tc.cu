@@ -14,6 +14,8 @@
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
 #include "decoder_simt.cuh"   // DS_* offsets of the FP32 "small" block (biases, heads, xyz taps)
+#include "photometric.cuh"
+#include "gn_step.cuh"
 
 namespace dfb {
 namespace tc {
@@ -473,25 +475,11 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
   epilogue_free(c);
 }
 
-__global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
-                                                      const int64_t* __restrict__ indexer, const float* __restrict__ latents,
-                                                      const float* __restrict__ obs_count, const void* __restrict__ blob, int robust,
-                                                      float robust_k, int with_J, double* __restrict__ packed,
-                                                      const GnShared* __restrict__ gs, int gi) {
-  if (gs) {                                      // device-resident Gauss-Newton: pose from the step kernel; a finished group returns at once
-    if (gs->done[gi]) return;
-    P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
-  }
-  Ctx c;
-#ifdef DFB_TC_PROFILE
-  c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
-#endif
-  PROF_MARK(c);                                  // kernel start
-  prologue(c, blob);
-  PROF_MARK(c);                                  // prologue done
-  float acc[HG_PER_THREAD];
-#pragma unroll
-  for (int k = 0; k < HG_PER_THREAD; ++k) acc[k] = 0.f;
+// SDF term over this group's tiles: transform -> map lookup -> decoder forward -> reverse pass -> Jacobian -> robust weight ->
+// per-thread partial sums (acc[HG_PER_THREAD]).  tracker.py:179-223.
+__device__ __forceinline__ void sdf_tiles(Ctx& c, const MapDev& M, const PoseDev& P, const float* __restrict__ obs, int n,
+                                          const int64_t* __restrict__ indexer, const float* __restrict__ latents,
+                                          const float* __restrict__ obs_count, int robust, float robust_k, int with_J, float* acc) {
   for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
     const int i = (int)(tile * T) + c.row;
     PROF_MARK(c);                                // tile start
@@ -525,10 +513,133 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
     if (valid) hg_accumulate_part(acc, J, r, robust_w(r, robust, robust_k), with_J != 0, c.part);
     PROF_MARK(c);                                // tile end
   }
+}
+
+__global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, const float* __restrict__ obs, int n,
+                                                      const int64_t* __restrict__ indexer, const float* __restrict__ latents,
+                                                      const float* __restrict__ obs_count, const void* __restrict__ blob, int robust,
+                                                      float robust_k, int with_J, double* __restrict__ packed) {
+  Ctx c;
+#ifdef DFB_TC_PROFILE
+  c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
+#endif
+  PROF_MARK(c);                                  // kernel start
+  prologue(c, blob);
+  PROF_MARK(c);                                  // prologue done
+  float acc[HG_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < HG_PER_THREAD; ++k) acc[k] = 0.f;
+  sdf_tiles(c, M, P, obs, n, indexer, latents, obs_count, robust, robust_k, with_J, acc);
   epilogue_free(c);
   PROF_MARK(c);
   block_reduce_parts(acc, c.part, packed, reinterpret_cast<double*>(c.sm + SM_A));
   PROF_MARK(c);                                  // kernel end
+}
+
+// One Gauss-Newton evaluation in ONE launch (gauss_newton.cu): the SDF term on the tensor cores; the photometric term's
+// pixels are handed out in chunks to whichever tile group has run out of tiles (in the last round half of the groups
+// have, and their SM's tensor pipe is busy with the sibling group anyway); both terms' sums go to GnShared with one
+// atomic per value per block; the last block to finish runs the step (solve, pose update, record for the host).
+constexpr int RGB_PIX = 2;                       // pixels per thread per chunk (chunk = GT * RGB_PIX pixels)
+__global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float* __restrict__ obs, int n, const int64_t* __restrict__ indexer,
+                                                       const float* __restrict__ latents, const float* __restrict__ obs_count,
+                                                       const void* __restrict__ blob, int robust, float robust_k, int with_J, RgbDev R,
+                                                       GnShared* gs, int gi, gn::StepArgs sa) {
+  if (gs->done[gi]) {                            // a launch queued ahead of a group that has ended: only the record is owed
+    if (blockIdx.x == 0 && threadIdx.x < 32) gn::skip_record(gs, sa);
+    return;
+  }
+  const PoseDev P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
+  Ctx c;
+#ifdef DFB_TC_PROFILE
+  c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
+#endif
+  PROF_MARK(c);                                  // kernel start
+  prologue(c, blob);
+  PROF_MARK(c);                                  // prologue done
+  float acc[HG_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < HG_PER_THREAD; ++k) acc[k] = 0.f;
+  sdf_tiles(c, M, P, obs, n, indexer, latents, obs_count, robust, robust_k, with_J, acc);
+  PROF_MARK(c);                                  // tiles done
+  float racc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) racc[k] = 0.f;
+  if (R.on) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R.P.k[i] = gs->krk[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) R.P.kt[i] = gs->kt[i];
+    const int tg = threadIdx.x % GT, npx = R.H * R.W;
+    volatile int* slotp = reinterpret_cast<volatile int*>(c.sm + SM_BAR + 32 + 4 * c.grp);
+    for (;;) {
+      if (tg == 0) *slotp = atomicAdd(&gs->rgb_cursor, 1);
+      group_sync(c.grp);
+      const int base = *slotp * (GT * RGB_PIX);
+      group_sync(c.grp);
+      if (base >= npx) break;
+#pragma unroll
+      for (int e = 0; e < RGB_PIX; ++e) {
+        const int i = base + e * GT + tg;
+        if (i < npx) {
+          const int v = i / R.W, u = i - v * R.W;
+          float f, J[6];
+          if (rgb_pixel(R.prev_I, R.prev_D, R.cur_I, R.cur_D, R.cur_G, R.H, R.W, R.P, v, u, with_J != 0, f, J)) {
+            if (with_J) {
+#pragma unroll
+              for (int a = 0; a < 6; ++a) J[a] = -J[a];   // tracker.py:162
+            }
+            hg_accumulate(racc, J, f, robust_w(f, R.robust, R.robust_k), with_J != 0);
+          }
+        }
+      }
+    }
+  }
+  PROF_MARK(c);                                  // pixels done
+  epilogue_free(c);                              // block-wide barrier; the tile buffers are scratch from here on
+  PROF_MARK(c);                                  // all groups done
+  // Block sums through shared memory (the tile buffers are idle): every thread writes its partial sums column-wise, then 8
+  // threads per value add their share in float64 and meet with three shuffles.  (A shuffle-only reduction of 45 doubles
+  // per thread is bound by the SM's one-warp-per-clock shuffle unit: measured 6.5 us here.)
+  {
+    constexpr int NS = HG_PER_THREAD * NPART;                     // 32 SDF rows (29 used); a row holds the GROUPS * T threads of one part
+    constexpr int LDS_ = GROUPS * T + 8, LDR = CTA_T + 8;         // padded rows: the 4 values a warp reads land in distinct banks
+    static_assert((NS * LDS_ + 29 * LDR) * 4 + gn::STEP_SCRATCH_BYTES <= GROUPS * SM_TILE_BYTES, "reduction scratch exceeds the tile buffers");
+    float* bs = reinterpret_cast<float*>(c.sm + SM_A);
+    float* br = bs + NS * LDS_;
+#pragma unroll
+    for (int k = 0; k < HG_PER_THREAD; ++k) bs[(c.part * HG_PER_THREAD + k) * LDS_ + c.grp * T + c.row] = acc[k];
+    if (R.on) {
+#pragma unroll
+      for (int k = 0; k < 29; ++k) br[k * LDR + threadIdx.x] = racc[k];
+    }
+    __syncthreads();
+    const int v = threadIdx.x >> 3, seg = threadIdx.x & 7;       // value, 1/8 of its row
+    double sacc = 0.0;
+    if (v < NS) {
+      const float* rowp = bs + v * LDS_ + seg;
+      double s1 = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < GROUPS * T / 8; j += 2) { sacc += (double)rowp[8 * j]; s1 += (double)rowp[8 * j + 8]; }
+      sacc += s1;
+    } else if (v < NS + 29 && R.on) {
+      const float* rowp = br + (v - NS) * LDR + seg;
+      double s1 = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < CTA_T / 8; j += 2) { sacc += (double)rowp[8 * j]; s1 += (double)rowp[8 * j + 8]; }
+      sacc += s1;
+    }
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1); sacc += __shfl_xor_sync(0xffffffffu, sacc, 2); sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+    if (seg == 0 && sacc != 0.0) {
+      if (v < 29) atomicAdd(&gs->sums[0][v], sacc);
+      else if (v >= NS && v < NS + 29) atomicAdd(&gs->sums[1][v - NS], sacc);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  PROF_MARK(c);                                  // sums out
+  gn::tail_step(gs, sa, c.sm + GROUPS * SM_TILE_BYTES + SM_A - gn::STEP_SCRATCH_BYTES, reinterpret_cast<int*>(c.sm + SM_BAR + 56));
+  PROF_MARK(c);                                  // kernel end (block 0; the step runs in whichever block finishes last)
 }
 
 __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restrict__ latents, const int64_t* __restrict__ occ, int B, int r,
@@ -623,13 +734,23 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
   return DFB_OK;
 }
 
+int tc_gn_eval(const MapDev& M, const float* obs, int n, const int64_t* indexer, const float* latents, const float* obs_count,
+               const void* blob, int robust, float robust_k, int with_J, const RgbDev& R, GnShared* gs, int gi, const gn::StepArgs& sa,
+               cudaStream_t s) {
+  int rc = tc::prep(tc::gn_eval_kernel);
+  if (rc) return rc;
+  const int grid = R.on ? sm_count() : std::max(1, tc::grid_for(n));     // every SM takes photometric chunks
+  tc::gn_eval_kernel<<<grid, tc::CTA_T, tc::SM_ALLOC, s>>>(M, obs, n, indexer, latents, obs_count, blob, robust, robust_k, with_J, R, gs, gi, sa);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
 int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const int64_t* indexer, const float* latents,
-              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, const GnShared* gs, int gi,
-              cudaStream_t s) {
+              const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s) {
   int rc = tc::prep(tc::sdf_hg_kernel);
   if (rc) return rc;
   tc::sdf_hg_kernel<<<tc::grid_for(n), tc::CTA_T, tc::SM_ALLOC, s>>>(M, P, obs, n, indexer, latents, obs_count, blob, robust, robust_k, with_J,
-                                                                   packed, gs, gi);
+                                                                   packed);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -14,159 +14,10 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gn_step.cuh"
 
 namespace {
-
-// All of this runs in one device thread (gn_step_kernel); loops have constant bounds and are unrolled so poses and the
-// 6x7 elimination tableau stay in registers (no local-memory traffic on the critical path between two evaluations).
-struct Pose {   // x -> R x + t, float64
-  double R[9], t[3];
-};
-
-__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
-}
-__device__ __forceinline__ void mat3_vec(const double* A, const double* v, double* o) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
-}
-__device__ __forceinline__ Pose compose(const Pose& a, const Pose& b) {   // a o b  (Isometry.dot)
-  Pose c;
-  mat3_mul(a.R, b.R, c.R);
-  double rt[3];
-  mat3_vec(a.R, b.t, rt);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) c.t[i] = rt[i] + a.t[i];
-  return c;
-}
-
-// The reference stores rotations as unit quaternions (pyquaternion normalises on every rotation_matrix access), which
-// re-orthonormalises the pose each iteration; do the same round trip.
-__device__ __forceinline__ void renormalise(double* R) {
-  double q0, q1, q2, q3;
-  const double tr = R[0] + R[4] + R[8];
-  if (tr > 0) {
-    const double s = sqrt(tr + 1.0) * 2;
-    q0 = 0.25 * s; q1 = (R[7] - R[5]) / s; q2 = (R[2] - R[6]) / s; q3 = (R[3] - R[1]) / s;
-  } else if (R[0] > R[4] && R[0] > R[8]) {
-    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
-    q0 = (R[7] - R[5]) / s; q1 = 0.25 * s; q2 = (R[1] + R[3]) / s; q3 = (R[2] + R[6]) / s;
-  } else if (R[4] > R[8]) {
-    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
-    q0 = (R[2] - R[6]) / s; q1 = (R[1] + R[3]) / s; q2 = 0.25 * s; q3 = (R[5] + R[7]) / s;
-  } else {
-    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
-    q0 = (R[3] - R[1]) / s; q1 = (R[2] + R[6]) / s; q2 = (R[5] + R[7]) / s; q3 = 0.25 * s;
-  }
-  const double n = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-  const double w = q0 / n, x = q1 / n, y = q2 / n, z = q3 / n;
-  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
-  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
-  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
-}
-
-__device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.py:205-228
-  Pose p;
-  const double* rho = xi;
-  const double* phi = xi + 3;
-  const double angle = sqrt(phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2]);
-  const double Wd[9] = {0, -phi[2], phi[1], phi[2], 0, -phi[0], -phi[1], phi[0], 0};
-  double J[9];
-  if (fabs(angle) <= 1e-8) {   // np.isclose(angle, 0.)
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { p.R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Wd[i]; J[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Wd[i]; }
-  } else {
-    const double ax[3] = {phi[0] / angle, phi[1] / angle, phi[2] / angle};
-    double s, c;
-    sincos(angle, &s, &c);
-    const double Wa[9] = {0, -ax[2], ax[1], ax[2], 0, -ax[0], -ax[1], ax[0], 0};
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double I = (i == j) ? 1.0 : 0.0, oo = ax[i] * ax[j];
-        p.R[3 * i + j] = c * I + (1 - c) * oo + s * Wa[3 * i + j];
-        J[3 * i + j] = (s / angle) * I + (1 - s / angle) * oo + ((1 - c) / angle) * Wa[3 * i + j];
-      }
-  }
-  renormalise(p.R);
-  mat3_vec(J, rho, p.t);
-  return p;
-}
-
-// np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular / non-finite.
-__device__ __forceinline__ bool solve6(const double* H, const double* g, double* x) {
-  double A[42];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) A[7 * (i) + (j)] = H[6 * i + j];
-    A[7 * (i) + (6)] = -g[i];
-  }
-  bool ok = true;
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    int piv = c;
-    double best = fabs(A[7 * (c) + (c)]);
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      const double v = fabs(A[7 * (r) + (c)]);
-      if (v > best) { best = v; piv = r; }
-    }
-    if (!(best > 0.0)) ok = false;
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      if (piv == r) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) { const double t = A[7 * (c) + (j)]; A[7 * (c) + (j)] = A[7 * (r) + (j)]; A[7 * (r) + (j)] = t; }
-      }
-    }
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      const double f = A[7 * (r) + (c)] / A[7 * (c) + (c)];
-#pragma unroll
-      for (int j = c; j < 7; ++j) A[7 * (r) + (j)] -= f * A[7 * (c) + (j)];
-    }
-  }
-#pragma unroll
-  for (int r = 5; r >= 0; --r) {
-    double sacc = A[7 * (r) + (6)];
-#pragma unroll
-    for (int j = r + 1; j < 6; ++j) sacc -= A[7 * (r) + (j)] * x[j];
-    x[r] = sacc / A[7 * (r) + (r)];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (!(fabs(x[i]) <= 1.79769313486231570e308)) ok = false;   // non-finite
-  return ok;
-}
-
-// float images of the current pose for the two term kernels (same casts as the host-side wrappers: tracker.py:145-147, :201)
-__device__ void publish_pose(dfb::GnShared* gs) {
-  Pose last, delta;
-  #pragma unroll
-  for (int i = 0; i < 9; ++i) { last.R[i] = gs->last[i]; delta.R[i] = gs->delta[i]; }
-  #pragma unroll
-  for (int i = 0; i < 3; ++i) { last.t[i] = gs->last[9 + i]; delta.t[i] = gs->delta[9 + i]; }
-  const Pose total = compose(last, delta);
-  float* hp = gs->pose_sdf;                                   // PoseDev: Rt(9) tt(3) Rd(9) td(3) Rl(9)
-  #pragma unroll
-  for (int i = 0; i < 9; ++i) { hp[i] = (float)total.R[i]; hp[12 + i] = (float)delta.R[i]; hp[24 + i] = (float)last.R[i]; }
-  #pragma unroll
-  for (int i = 0; i < 3; ++i) { hp[9 + i] = (float)total.t[i]; hp[21 + i] = (float)delta.t[i]; }
-  const double fx = gs->intr[0], fy = gs->intr[1], cx = gs->intr[2], cy = gs->intr[3];
-  const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-  const double Kinv[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
-  double KR[9], KRK[9], Kt[3];
-  mat3_mul(K, delta.R, KR); mat3_mul(KR, Kinv, KRK); mat3_vec(K, delta.t, Kt);
-  #pragma unroll
-  for (int i = 0; i < 9; ++i) gs->krk[i] = (float)KRK[i];
-  #pragma unroll
-  for (int i = 0; i < 3; ++i) gs->kt[i] = (float)Kt[i];
-}
+using namespace dfb::gn;
 
 struct GnInit {
   double last[12], delta[12], intr[4];
@@ -178,108 +29,15 @@ __global__ void gn_init_kernel(dfb::GnShared* gs, GnInit in) {
   if (t < 12) { gs->last[t] = in.last[t]; gs->delta[t] = in.delta[t]; gs->last_delta[t] = in.delta[t]; }
   if (t < 4) gs->intr[t] = in.intr[t];
   if (t < 8) gs->done[t] = 0;
-  if (t == 0) { gs->error = 0; gs->last_energy = CUDART_INF; }
+  if (t == 0) { gs->error = 0; gs->last_energy = CUDART_INF; gs->ticket = 0; gs->rgb_cursor = 0; gs->pad_ = 0; }
   __syncthreads();
   if (t == 0) publish_pose(gs);
 }
 
-// One Gauss-Newton step (the body of the loop at tracker.py:240-281) for group gi, iteration `step` (step == n_it is the
-// evaluation-only pass, i_iter = -1).  One warp: the state is staged through shared memory (one round of global loads
-// and one of stores, all lanes), the 36 + 6 normal-equation entries are scaled and summed lane-parallel, and lane 0 runs
-// the float64 solve and pose update out of registers.
-__global__ void __launch_bounds__(32) gn_step_kernel(dfb::GnShared* __restrict__ gs, dfb::GnRecord* __restrict__ ring, int seq, int gi, int step,
-                                                     int n_it, int use_sdf, int use_rgb, double rgb_weight) {
-  __shared__ dfb::GnShared sh;
-  __shared__ double Hs[36], gsv[6];
-  __shared__ int flags[2];                       // executed, broke
-  static_assert(sizeof(dfb::GnShared) % 8 == 0, "GnShared is copied as doubles");
-  constexpr int ND = sizeof(dfb::GnShared) / 8;
-  const int lane = threadIdx.x;
-  dfb::GnRecord* rec = ring + (seq & 3);
-  {
-    const double* src = reinterpret_cast<const double*>(gs);
-    double* dst = reinterpret_cast<double*>(&sh);
-    for (int i = lane; i < ND; i += 32) dst[i] = src[i];
-  }
-  __syncwarp();
-  const bool run = !sh.done[gi];
-  const bool no_grad = (step == n_it);
-  double cnt0 = 0.0, cnt1 = 0.0;
-  if (run) {
-    cnt0 = use_sdf ? sh.sums[0][28] : 0.0;
-    cnt1 = use_rgb ? sh.sums[1][28] : 0.0;
-    const double scale0 = 1.0 / cnt0, scale1 = rgb_weight / cnt1;   // tracker.py:215 / :170 (inf/NaN when nothing is valid, like 1/0 there)
-    if (!no_grad) {
-      for (int e = lane; e < 42; e += 32) {                          // SDF term first, then the photometric term (tracker.py:248-262)
-        int idx;
-        if (e < 36) {
-          const int a = e / 6, b = e % 6, lo = a < b ? a : b, hi = a < b ? b : a;
-          idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
-        } else {
-          idx = 21 + (e - 36);
-        }
-        double v = 0.0;
-        if (use_sdf) v += sh.sums[0][idx] * scale0;
-        if (use_rgb) v += sh.sums[1][idx] * scale1;
-        if (e < 36) Hs[e] = v; else gsv[e - 36] = v;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {
-      double energy = 0.0;
-      if (use_sdf) energy += sh.sums[0][27] * scale0;
-      if (use_rgb) energy += sh.sums[1][27] * scale1;
-      int broke = 0;
-      const double last_energy = step == 0 ? CUDART_INF : sh.last_energy;
-      if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
-#pragma unroll
-        for (int i = 0; i < 12; ++i) sh.delta[i] = sh.last_delta[i];
-        sh.done[gi] = 1;
-        broke = 1;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) sh.last_delta[i] = sh.delta[i];
-        sh.last_energy = energy;
-        if (!no_grad) {
-          double xi[6];
-          if (!solve6(Hs, gsv, xi)) {
-            sh.error = 1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sh.done[i] = 1;
-          } else {
-            Pose d;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) d.R[i] = sh.delta[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) d.t[i] = sh.delta[9 + i];
-            Pose nd = compose(from_twist(xi), d);                     // tracker.py:277-278
-            renormalise(nd.R);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) sh.delta[i] = nd.R[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) sh.delta[9 + i] = nd.t[i];
-          }
-        } else {
-          sh.done[gi] = 1;                                            // the evaluation-only pass closes the group
-        }
-      }
-      publish_pose(&sh);
-      flags[1] = broke;
-    }
-    __syncwarp();
-    for (int i = lane; i < 64; i += 32) reinterpret_cast<double*>(sh.sums)[i] = 0.0;   // zero-invariant for the next evaluation
-    __syncwarp();
-    double* dst = reinterpret_cast<double*>(gs);
-    const double* src = reinterpret_cast<const double*>(&sh);
-    for (int i = lane; i < ND; i += 32) dst[i] = src[i];
-  }
-  // record for the host (pinned memory): payload from all lanes, then a system-wide fence, then the sequence number
-  if (lane < 12) rec->delta[lane] = sh.delta[lane];
-  if (lane == 12) { rec->executed = run ? 1 : 0; rec->broke = run ? flags[1] : 0; rec->error = sh.error; }
-  if (lane == 13) { rec->cnt[0] = cnt0; rec->cnt[1] = cnt1; }
-  __threadfence_system();                        // every lane: its payload stores are visible system-wide ...
-  __syncwarp();                                  // ... before lane 0 publishes the sequence number
-  if (lane == 0) *reinterpret_cast<volatile int*>(&rec->seq) = seq;
+// Stand-alone step kernel (used after the FP32-engine SDF term, whose kernel has no fused tail).
+__global__ void __launch_bounds__(32) gn_step_kernel(dfb::GnShared* gs, StepArgs a) {
+  __shared__ __align__(16) unsigned char scratch[STEP_SCRATCH_BYTES];
+  step_warp(gs, a, scratch);
 }
 
 }  // namespace
@@ -318,9 +76,10 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
   DFB_LAUNCH_CHECK();
   const float intr4[4] = {(float)init.intr[0], (float)init.intr[1], (float)init.intr[2], (float)init.intr[3]};
 
+  const bool tc_engine = dfb_get_decoder_engine() == 1;
   static int seq_base = 0;                                          // records carry a process-unique, non-zero sequence number
   struct Slot { int seq, gi, step, sdf_event; };
-  int n_sdf = 0, n_rgb = 0, n_steps = 0, i_iter = 0, n_events = 0, error = 0;
+  int n_sdf = 0, n_rgb = 0, n_launches = 1 /* gn_init_kernel */, i_iter = 0, n_events = 0, error = 0;
   double sdf_ms = 0.0, sdf_q_j = 0.0, sdf_q_nj = 0.0;
   double delta_out[12];
   memcpy(delta_out, h_delta_pose, sizeof(delta_out));
@@ -332,19 +91,40 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     out.gi = gi; out.step = step; out.sdf_event = -1;
     if (++seq_base == 0 || seq_base == INT32_MAX) seq_base = 1;
     out.seq = seq_base;
-    if (h_cfg->use_sdf[gi]) {
+    const int use_sdf = h_cfg->use_sdf[gi] ? 1 : 0, use_rgb = lvl >= 0 ? 1 : 0;
+    const StepArgs sa = {ring, out.seq, gi, step, n_it, use_sdf, use_rgb, (double)h_cfg->rgb_weight};
+    if (use_sdf && tc_engine) {
+      // ONE launch per evaluation: SDF tiles on the tensor cores, photometric pixels work-stolen by idle tile groups,
+      // and the step as the tail of the last block (decoder_tc.cu)
+      if (timing) { out.sdf_event = n_events; cudaEventRecord(event(2 * n_events), s); }
+      int rc = dfb::launch_sdf_rgb_gn(h_params, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
+                                      h_cfg->sdf_robust_k, no_grad ? 0 : 1, use_rgb ? &h_levels[lvl] : nullptr, intr4,
+                                      h_cfg->rgb_min_grad_scale, h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust, h_cfg->rgb_robust_k, gs, gi,
+                                      &sa, s);
+      if (rc) return rc;
+      ++n_launches;
+      if (timing) { cudaEventRecord(event(2 * n_events + 1), s); ++n_events; }
+      return DFB_OK;
+    }
+    if (!use_sdf && use_rgb) {                   // photometric-only group: one launch, step as the tail of the last block
+      ++n_launches;
+      return dfb::launch_rgb_step_gn(&h_levels[lvl], intr4, h_cfg->rgb_min_grad_scale, h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust,
+                                     h_cfg->rgb_robust_k, no_grad ? 0 : 1, gs, gi, &sa, s);
+    }
+    n_launches += (use_sdf && n > 0 ? 1 : 0) + use_rgb + 1;
+    if (use_sdf) {                               // FP32 CUDA-core engine: term kernels, then the stand-alone step kernel
       if (timing) { out.sdf_event = n_events; cudaEventRecord(event(2 * n_events), s); }
       int rc = dfb::launch_sdf_hg_gn(h_params, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
                                      h_cfg->sdf_robust_k, no_grad ? 0 : 1, gs, gi, s);
       if (rc) return rc;
       if (timing) { cudaEventRecord(event(2 * n_events + 1), s); ++n_events; }
     }
-    if (lvl >= 0) {
+    if (use_rgb) {
       int rc = dfb::launch_rgb_hg_gn(&h_levels[lvl], intr4, h_cfg->rgb_min_grad_scale, h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust,
                                      h_cfg->rgb_robust_k, no_grad ? 0 : 1, gs, gi, s);
       if (rc) return rc;
     }
-    gn_step_kernel<<<1, 32, 0, s>>>(gs, ring, out.seq, gi, step, n_it, h_cfg->use_sdf[gi] ? 1 : 0, lvl >= 0 ? 1 : 0, (double)h_cfg->rgb_weight);
+    gn_step_kernel<<<1, 32, 0, s>>>(gs, sa);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   };
@@ -373,11 +153,11 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     const int n_it = h_cfg->n_iter[sl.gi];
     const bool no_grad = (sl.step == n_it);
     i_iter = no_grad ? -1 : sl.step;
-    ++n_steps;
     if (h_cfg->use_sdf[sl.gi]) {
       ++n_sdf;
       if (timing && sl.sdf_event >= 0) {
         float ms = 0.f;
+        cudaEventSynchronize(event(2 * sl.sdf_event + 1));   // the record is written by the kernel's last block, just before it exits
         cudaEventElapsedTime(&ms, event(2 * sl.sdf_event), event(2 * sl.sdf_event + 1));
         sdf_ms += ms;
         (no_grad ? sdf_q_nj : sdf_q_j) += r.cnt[0];
@@ -427,6 +207,6 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     h_stats[5] = (int32_t)sdf_q_j;               // valid queries evaluated with the reverse pass
     h_stats[6] = (int32_t)sdf_q_nj;              // valid queries evaluated forward-only
   }
-  h_stats[7] = n_steps;                          // evaluations executed (= step kernels that did work)
+  h_stats[7] = n_launches;                       // kernels launched by this call (including look-ahead launches that returned at once)
   return DFB_OK;
 }

@@ -1,6 +1,8 @@
 // Photometric term: Sobel gradients, per-pixel residual/Jacobian (drop-in ops) and the fused H/g reduction.
 // Reference: system/ext/imgproc/photometric.cu:3-138, system/tracker.py:136-177.
 #include "common.cuh"
+#include "photometric.cuh"
+#include "gn_step.cuh"
 
 namespace dfb {
 
@@ -19,44 +21,6 @@ __global__ void __launch_bounds__(256) gradient_xy_kernel(const float* __restric
   g[2 * i] = (u_d1 + 2 * u_d2 + u_d3) / 8.0f;
   float v_d1 = r2[-1] - r0[-1], v_d2 = r2[0] - r0[0], v_d3 = r2[1] - r0[1];
   g[2 * i + 1] = (v_d1 + 2 * v_d2 + v_d3) / 8.0f;
-}
-
-struct RgbParams {
-  float k[9];
-  float kt[3];
-  float fx, fy, cx, cy;
-  float min_grad_scale, max_depth_delta;
-};
-
-// photometric.cu:24-77 for one pixel.  Returns validity; f and J[6] filled when valid.
-__device__ __forceinline__ bool rgb_pixel(const float* __restrict__ prev_I, const float* __restrict__ prev_D,
-                                          const float* __restrict__ cur_I, const float* __restrict__ cur_D,
-                                          const float* __restrict__ dIdxy, int H, int W, const RgbParams& P, int v, int u,
-                                          bool want_J, float& f, float* J) {
-  int i = v * W + u;
-  float dI_dx = dIdxy[2 * i], dI_dy = dIdxy[2 * i + 1];
-  float mTwo = (dI_dx * dI_dx) + (dI_dy * dI_dy);
-  if (mTwo < P.min_grad_scale || isnan(mTwo)) return false;
-  float d1 = cur_D[i];
-  if (isnan(d1)) return false;
-  float warpped_d1 = d1 * (P.k[6] * u + P.k[7] * v + P.k[8]) + P.kt[2];
-  int u0 = __float2int_rn((d1 * (P.k[0] * u + P.k[1] * v + P.k[2]) + P.kt[0]) / warpped_d1);
-  int v0 = __float2int_rn((d1 * (P.k[3] * u + P.k[4] * v + P.k[5]) + P.kt[1]) / warpped_d1);
-  if (!(u0 >= 0 && u0 < W && v0 >= 0 && v0 < H)) return false;
-  float d0 = prev_D[v0 * W + u0];
-  if (!(!isnan(d0) && fabsf(warpped_d1 - d0) <= P.max_depth_delta && d0 > 0.0f)) return false;
-  f = cur_I[i] - prev_I[v0 * W + u0];
-  if (want_J) {
-    float Gx = d0 * (u0 - P.cx) / P.fx, Gy = d0 * (v0 - P.cy) / P.fy, Gz = d0;
-    float p0 = dI_dx * P.fx / Gz;
-    float p1 = dI_dy * P.fy / Gz;
-    float p2 = -(p0 * Gx + p1 * Gy) / Gz;
-    J[0] = p0; J[1] = p1; J[2] = p2;
-    J[3] = -Gz * p1 + Gy * p2;
-    J[4] = Gz * p0 - Gx * p2;
-    J[5] = -Gy * p0 + Gx * p1;
-  }
-  return true;
 }
 
 __global__ void __launch_bounds__(256) rgb_odometry_kernel(const float* prev_I, const float* prev_D, const float* cur_I,
@@ -164,6 +128,65 @@ int dfb_rgb_hg(const float* prev_I, const float* prev_D, const float* cur_I, con
 }
 
 }  // extern "C"
+
+// Photometric-only evaluation (first group of fusion-lr-kt.yaml): pixels -> block sums -> atomics, and the last block to
+// finish runs the Gauss-Newton step.  PIX pixels per thread (1 for the small pyramid levels: latency matters, not occupancy).
+namespace dfb {
+template <int PIX>
+__global__ void __launch_bounds__(HG_T) rgb_step_gn_kernel(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D,
+                                                           const float* dIdxy, int H, int W, RgbParams P, int robust, float robust_k,
+                                                           int with_J, GnShared* gs, int gi, gn::StepArgs sa) {
+  __shared__ __align__(16) unsigned char scratch[gn::STEP_SCRATCH_BYTES];
+  __shared__ int flag;
+  if (gs->done[gi]) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) gn::skip_record(gs, sa);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P.k[i] = gs->krk[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P.kt[i] = gs->kt[i];
+  float acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+  const int base = blockIdx.x * (HG_T * PIX) + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < PIX; ++e) {
+    const int i = base + e * HG_T;
+    if (i < H * W) {
+      const int v = i / W, u = i - v * W;
+      float f, J[6];
+      if (rgb_pixel(prev_I, prev_D, cur_I, cur_D, dIdxy, H, W, P, v, u, with_J != 0, f, J)) {
+        if (with_J) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) J[a] = -J[a];   // tracker.py:162
+        }
+        hg_accumulate(acc, J, f, robust_w(f, robust, robust_k), with_J != 0);
+      }
+    }
+  }
+  block_reduce_atomic<29, HG_T>(acc, gs->sums[1]);
+  __threadfence();
+  __syncthreads();
+  gn::tail_step(gs, sa, scratch, &flag);
+}
+
+int launch_rgb_step_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
+                       int compute_J, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s) {
+  RgbParams P = {};
+  P.fx = intr4[0]; P.fy = intr4[1]; P.cx = intr4[2]; P.cy = intr4[3];
+  P.min_grad_scale = min_grad_scale; P.max_depth_delta = max_depth_delta;
+  const long long npx = (long long)L->H * L->W;
+  if (npx >= 4LL * HG_T * 148)
+    rgb_step_gn_kernel<4><<<div_up(npx, HG_T * 4), HG_T, 0, s>>>(L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust,
+                                                                robust_k, compute_J, gs, gi, *sa);
+  else
+    rgb_step_gn_kernel<1><<<div_up(npx, HG_T), HG_T, 0, s>>>(L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust,
+                                                            robust_k, compute_J, gs, gi, *sa);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+}  // namespace dfb
 
 // Photometric term of one device-resident Gauss-Newton evaluation: K R K^-1 and K t come from `gs`, sums go to gs->sums[1].
 namespace dfb {

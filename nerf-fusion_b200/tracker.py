@@ -282,8 +282,7 @@ class SDFTracker:
         self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
         if self.time_kernels:
             self.sdf_kernel_us += stats[4]; self.sdf_queries_J += stats[5]; self.sdf_queries_noJ += stats[6]
-        _lib.CALLS["gn_term"] = _lib.CALLS.get("gn_term", 0) + stats[1] + stats[2]      # launches made inside the C driver
-        _lib.CALLS["gn_step"] = _lib.CALLS.get("gn_step", 0) + stats[7]
+        _lib.CALLS["gn_kernel"] = _lib.CALLS.get("gn_kernel", 0) + stats[7]            # launches made inside the C driver
         d = np.array(list(deltap), dtype=np.float64)
         new_delta = Isometry.from_matrix(d[:9].reshape(3, 3), d[9:12])
         if stats[0] >= 10:

@@ -224,43 +224,24 @@ __device__ float4 sym3eig_smallest(float3 x1, float3 x2, float3 x3) {
 }
 
 // K nearest (self included) kept sorted ascending in registers; then pcproc.cu:107-158.
+// An entry is one 64-bit key: (distance bits << 32) | ORIGINAL index.  Distances are >= +0, so their bit patterns order
+// like the values, and one unsigned compare implements "closer, or equally close and earlier in the input" -- the
+// tie-break that makes the result independent of the atomics-defined order inside a grid cell and of the visiting
+// order (equal distances are common on a pixel lattice).  Coordinates are re-read from the input array by that index.
 template <int K>
-__global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ sorted, int n, const GridParams* gpp,
-                                                      const int* __restrict__ cell_start, int max_nn, float radius,
-                                                      float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
+__global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
+                                                         const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
+                                                         float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
   if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   GridParams g = *gpp;
   float4 q = sorted[j];
   int3 c = cell_coord(g, q.x, q.y, q.z);
-  float kd[K];
-  int ki[K], ko[K];   // sorted-array position and ORIGINAL index (the tie-break that makes the result independent of the
-                      // atomics-defined order inside a grid cell and of the visiting order; equal distances are common
-                      // on a pixel lattice)
+  unsigned long long key[K];
 #pragma unroll
-  for (int t = 0; t < K; ++t) { kd[t] = CUDART_INF_F; ki[t] = -1; ko[t] = 0x7fffffff; }
+  for (int t = 0; t < K; ++t) key[t] = 0x7f8000007fffffffull;       // (+inf, INT_MAX)
   const float r2 = radius * radius;
-  auto scan = [&](int b, int e) {
-    for (int k = b; k < e; ++k) {
-      float4 p = sorted[k];
-      float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-      // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
-      // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
-      const int o = __float_as_int(p.w);
-      if (d < r2 && (d < kd[K - 1] || (d == kd[K - 1] && o < ko[K - 1]))) {
-        kd[K - 1] = d; ki[K - 1] = k; ko[K - 1] = o;
-#pragma unroll
-        for (int t = K - 1; t > 0; --t) {
-          if (kd[t] < kd[t - 1] || (kd[t] == kd[t - 1] && ko[t] < ko[t - 1])) {
-            float td = kd[t]; kd[t] = kd[t - 1]; kd[t - 1] = td;
-            int ti = ki[t]; ki[t] = ki[t - 1]; ki[t - 1] = ti;
-            int to = ko[t]; ko[t] = ko[t - 1]; ko[t - 1] = to;
-          }
-        }
-      }
-    }
-  };
   // Expanding shells of cells around the query's cell (the grid is finer than the radius).  After the block [c-R, c+R]^3
   // has been scanned every unvisited point is farther than R * cell from the query, so once the last entry that will
   // be used is closer than that (with a margin for the rounding of cell_coord) the list is final: the exact K nearest.
@@ -274,25 +255,49 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
         const int y = c.y + dy;
         if (y < 0 || y >= g.ny) continue;
         const int row = (x * g.ny + y) * g.nz;
-        if (R == 1 || dx == -R || dx == R || dy == -R || dy == R) {      // whole z-run (contiguous in memory)
-          const int z0 = max(c.z - R, 0), z1 = min(c.z + R, g.nz - 1);
-          scan(cell_start[row + z0], cell_start[row + z1 + 1]);
-        } else {                                                          // interior column: only the two new end cells
-          if (c.z - R >= 0) scan(cell_start[row + c.z - R], cell_start[row + c.z - R + 1]);
-          if (c.z + R < g.nz) scan(cell_start[row + c.z + R], cell_start[row + c.z + R + 1]);
+        // R == 1 or a column on the shell's side faces: the whole z-run (contiguous in memory); interior column: only the
+        // two new end cells
+        const bool whole = (R == 1 || dx == -R || dx == R || dy == -R || dy == R);
+        for (int sgm = 0; sgm < 2; ++sgm) {
+          int za, zb;
+          if (whole) {
+            if (sgm) break;
+            za = max(c.z - R, 0); zb = min(c.z + R, g.nz - 1);
+          } else {
+            za = zb = sgm ? c.z + R : c.z - R;
+            if (za < 0 || za >= g.nz) continue;
+          }
+          const int b = cell_start[row + za], e = cell_start[row + zb + 1];
+          for (int k = b; k < e; ++k) {
+            const float4 p = sorted[k];
+            const float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+            // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
+            // self entry (d = 0) must occupy slot 0; d < r2 keeps self.
+            const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+            if (d < r2 && nk < key[K - 1]) {
+              key[K - 1] = nk;
+#pragma unroll
+              for (int t = K - 1; t > 0; --t) {
+                const unsigned long long a = key[t - 1], bb = key[t];
+                const bool sw = bb < a;
+                key[t - 1] = sw ? bb : a;
+                key[t] = sw ? a : bb;
+              }
+            }
+          }
         }
       }
     }
     const float reach = (float)R * g.cell * 0.9999f;
-    if (kd[last] < reach * reach) break;
+    if (__uint_as_float((unsigned)(key[last] >> 32)) < reach * reach) break;
   }
   int oi = __float_as_int(q.w);
   float3 mean = make_float3(0.f, 0.f, 0.f);
   float valid = 0.f;
 #pragma unroll
   for (int t = 1; t < K; ++t) {
-    if (t < max_nn && kd[t] < r2) {
-      float4 p = sorted[ki[t]];
+    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
+      float4 p = pc4[(unsigned)key[t]];
       mean.x += p.x; mean.y += p.y; mean.z += p.z;
       valid += 1.0f;
     }
@@ -305,8 +310,8 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
 #pragma unroll
   for (int t = 1; t < K; ++t) {
-    if (t < max_nn && kd[t] < r2) {
-      float4 pp = sorted[ki[t]];
+    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
+      float4 pp = pc4[(unsigned)key[t]];
       float3 pos = make_float3(pp.x - mean.x, pp.y - mean.y, pp.z - mean.z);
       c1.x += pos.x * pos.x; c1.y += pos.x * pos.y; c1.z += pos.x * pos.z;
       c2.x += pos.y * pos.x; c2.y += pos.y * pos.y; c2.z += pos.y * pos.z;
@@ -597,9 +602,9 @@ int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, cons
   if (rc) return rc;
   float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16)
-    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pc4), n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
   else
-    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pc4), n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -747,9 +752,9 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   if (rc) return rc;
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16)
-    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
   else
-    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
   flag_from_normals_kernel<<<div_up(n, 256), 256, 0, s>>>(nrmC, n, &counts[1], flag);
   DFB_LAUNCH_CHECK();
   rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s);

@@ -68,9 +68,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
   return r;
 }
 
+// n_dev (optional): device-side length, n is then only the upper bound the grid was sized for; tiles past the device
+// length return at once, so a scan over a mostly unused capacity costs what its used part costs.
 template <bool POPC>
-__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const void* in, int n, int* block_sums) {
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const void* in, int n, int* block_sums, const int* __restrict__ n_dev) {
   __shared__ int tot;
+  if (n_dev) n = min(n, *n_dev);
+  if (blockIdx.x * SCAN_TILE >= n) return;
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
   int s = 0;
 #pragma unroll
@@ -79,8 +83,9 @@ __global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const void* in, int n, 
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(SCAN_T) scan_of_sums(int* block_sums, int nb, int* total) {
+__global__ void __launch_bounds__(SCAN_T) scan_of_sums(int* block_sums, int nb, int* total, const int* __restrict__ n_dev) {
   __shared__ int tot;
+  if (n_dev) nb = min(nb, (*n_dev + SCAN_TILE - 1) / SCAN_TILE);
   int carry = 0;
   for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
     int i = b0 + threadIdx.x;
@@ -97,8 +102,10 @@ __global__ void __launch_bounds__(SCAN_T) scan_of_sums(int* block_sums, int nb, 
 }
 
 template <bool POPC>
-__global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, int n, const int* block_sums) {
+__global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, int n, const int* block_sums, const int* __restrict__ n_dev) {
   __shared__ int tot;
+  if (n_dev) n = min(n, *n_dev);
+  if (blockIdx.x * SCAN_TILE >= n) return;
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
   int v[SCAN_E];
   int s = 0;
@@ -116,24 +123,35 @@ __global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, i
 }
 
 template <bool POPC>
-static int scan_impl(const void* in, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
+static int scan_impl(const void* in, int* out, int n, int* block_sums, int* total, const int* n_dev, cudaStream_t s) {
   if (n <= 0) {
     if (total) DFB_CUDA(cudaMemsetAsync(total, 0, sizeof(int), s));
     return DFB_OK;
   }
   int nb = div_up(n, SCAN_TILE);
-  scan_tile_sums<POPC><<<nb, SCAN_T, 0, s>>>(in, n, block_sums);
-  scan_of_sums<<<1, SCAN_T, 0, s>>>(block_sums, nb, total);
-  scan_apply<POPC><<<nb, SCAN_T, 0, s>>>(in, out, n, block_sums);
+  scan_tile_sums<POPC><<<nb, SCAN_T, 0, s>>>(in, n, block_sums, n_dev);
+  scan_of_sums<<<1, SCAN_T, 0, s>>>(block_sums, nb, total, n_dev);
+  scan_apply<POPC><<<nb, SCAN_T, 0, s>>>(in, out, n, block_sums, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
 
-int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
-  return scan_impl<false>(in, out, n, block_sums, total, s);
+int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s, const int* n_dev) {
+  return scan_impl<false>(in, out, n, block_sums, total, n_dev, s);
 }
-int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s) {
-  return scan_impl<true>(words, out, n, block_sums, total, s);
+int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s, const int* n_dev) {
+  return scan_impl<true>(words, out, n, block_sums, total, n_dev, s);
+}
+
+// zero the first *n_dev (<= n_max) 32-bit words
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ p, int n_max, const int* __restrict__ n_dev) {
+  const int n = min(n_max, *n_dev);
+  const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i + 3 < n) *reinterpret_cast<uint4*>(p + i) = make_uint4(0, 0, 0, 0);
+  else for (int k = i; k < n; ++k) p[k] = 0;
+}
+void zero_words_dev(void* p, int n_max, const int* n_dev, cudaStream_t s) {
+  zero_words_kernel<<<div_up(n_max, 1024), 256, 0, s>>>(reinterpret_cast<uint32_t*>(p), n_max, n_dev);
 }
 
 // expands the packed 29 doubles (21 upper-tri, 6, 1, 1) into the public 44-double layout

@@ -107,9 +107,11 @@ __device__ __forceinline__ float div_vs(float x, float vs, float inv_vs, int div
 // exclusive scan of int32 (3 kernels, any n).  block_sums: ceil(n/2048)+1 ints of scratch.
 // total (sum of all) is written to *total if non-null.
 // ------------------------------------------------------------------------------------------------
-int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s);
-// same but the input is popcount(words[i])
-int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s);
+int exclusive_scan_i32(const int* in, int* out, int n, int* block_sums, int* total, cudaStream_t s, const int* n_dev = nullptr);
+// same over popcounts of 32-bit words
+int exclusive_scan_popc(const uint32_t* words, int* out, int n, int* block_sums, int* total, cudaStream_t s, const int* n_dev = nullptr);
+// zero the first *n_dev (<= n_max) 32-bit words of p (16-byte aligned) without a host-side length
+void zero_words_dev(void* p, int n_max, const int* n_dev, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // Gauss-Newton reduction helpers shared by the SDF and photometric terms

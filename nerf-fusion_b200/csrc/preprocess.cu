@@ -42,6 +42,7 @@ constexpr int NORMAL_SUB = 4;            // the kNN grid of estimate_normals use
 struct GridParams {
   float ox, oy, oz, cell, inv_cell;
   int nx, ny, nz, ncell;
+  int ncell1;          // ncell + 1: device-side length of the count / start arrays
 };
 
 struct GridWs {
@@ -117,7 +118,7 @@ __global__ void grid_params_kernel(const unsigned* bbox, float radius, int cap, 
   }
   gp->ox = lo[0]; gp->oy = lo[1]; gp->oz = lo[2];
   gp->cell = cell; gp->inv_cell = 1.0f / cell;
-  gp->nx = nx; gp->ny = ny; gp->nz = nz; gp->ncell = nx * ny * nz;
+  gp->nx = nx; gp->ny = ny; gp->nz = nz; gp->ncell = nx * ny * nz; gp->ncell1 = gp->ncell + 1;
 }
 
 __device__ __forceinline__ int3 cell_coord(const GridParams& g, float x, float y, float z) {
@@ -248,10 +249,14 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
   const int Rmax = max(1, (int)ceilf(radius * g.inv_cell));
   const int last = min(max_nn, K) - 1;
   for (int R = 1; R <= Rmax; ++R) {
-    for (int dx = -R; dx <= R; ++dx) {
+    // columns nearest to the query first (0, -1, +1, -2, ...): the K-th distance tightens early and most later
+    // candidates fail the cheap test
+    for (int ix = 0; ix <= 2 * R; ++ix) {
+      const int dx = (ix & 1) ? -((ix + 1) >> 1) : (ix >> 1);
       const int x = c.x + dx;
       if (x < 0 || x >= g.nx) continue;
-      for (int dy = -R; dy <= R; ++dy) {
+      for (int iy = 0; iy <= 2 * R; ++iy) {
+        const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
         const int y = c.y + dy;
         if (y < 0 || y >= g.ny) continue;
         const int row = (x * g.ny + y) * g.nz;
@@ -332,12 +337,13 @@ static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, c
   bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
   grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp);
-  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (cap + 1), s));
+  // counts, scan and cursor reset cover the ncell + 1 cells the bounding box needs (device-side length), not the capacity
+  zero_words_dev(w.cell_count, cap + 1, &w.gp->ncell1, s);
   grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev);
   DFB_LAUNCH_CHECK();
-  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s);
+  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s, &w.gp->ncell1);
   if (rc) return rc;
-  DFB_CUDA(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (cap + 1), s));
+  zero_words_dev(w.cell_count, cap + 1, &w.gp->ncell1, s);
   grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
@@ -430,6 +436,7 @@ struct BoxParams {
   long long nx, ny, nz;
   int n_words;
   int overflow;
+  int n_zero;          // n_words + 1: words of the bitmap to clear
 };
 constexpr long long BOX_BITS_CAP = 1ll << 27;  // 16 MiB bitmap
 
@@ -451,6 +458,7 @@ __global__ void box_params_kernel(const unsigned* bbox, float voxel_size, int di
   bp->overflow = bits > BOX_BITS_CAP ? 1 : 0;
   if (bp->overflow) bits = 0;
   bp->n_words = (int)((bits + 31) / 32);
+  bp->n_zero = bp->n_words + 1;
 }
 
 __global__ void __launch_bounds__(256) box_key_kernel(const float* __restrict__ pts, int n, float voxel_size,
@@ -672,10 +680,10 @@ static int box_filter_impl(const float* points, const float* normals, int n, con
   bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(points, n, 3, bbox, n_dev);
   box_params_kernel<<<1, 1, 0, s>>>(bbox, voxel_size, div_mode, bp);
-  DFB_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)(max_words + 1), s));
+  zero_words_dev(bits, max_words + 1, &bp->n_zero, s);        // only the words this frame's bounding box uses
   box_key_kernel<<<div_up(n, 256), 256, 0, s>>>(points, n, voxel_size, div_mode, bp, keys, bits, n_dev);
   DFB_LAUNCH_CHECK();
-  int rc = exclusive_scan_popc(bits, word_rank, max_words, bsums, d_n_out, s);
+  int rc = exclusive_scan_popc(bits, word_rank, max_words, bsums, d_n_out, s, &bp->n_words);
   if (rc) return rc;
   box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank, n_dev);
   DFB_LAUNCH_CHECK();

@@ -151,8 +151,7 @@ def gen_frames(dfb, n, device, seed):
 
 def refresh(dfb, m, trk, frame_id, depth, rgb, calib, first_iso, integrate_interval=20, depth_cut=(0.5, 5.0)):
     """main.py:42-102 without the GUI: depth cut, track, integrate every `integrate_interval` frames."""
-    depth = torch.where((depth < depth_cut[0]) | (depth > depth_cut[1]), torch.full_like(depth, float("nan")), depth)
-    pose = trk.track_camera(rgb, depth, calib, first_iso if len(trk.all_pd_pose) == 0 else None)
+    pose = trk.track_camera(rgb, depth, calib, first_iso if len(trk.all_pd_pose) == 0 else None, depth_cut=depth_cut)
     pc, nrm = trk.last_processed_pc
     if frame_id % integrate_interval == 0:
         m.integrate_keyframe(pose @ pc, pose.rotation @ nrm, do_optimize=False)

@@ -117,24 +117,29 @@ class SDFTracker:
             pc_data = pc_data[ok, :3].contiguous()
         return point_box_filter(pc_data, normal_data, 0.02, self.map.div_mode)
 
-    def _frontend(self, rgb_data, depth_data, calib):
-        """Everything of tracker.py:75-120 that needs no host decision: intensity, pyramids, gradients, preprocessing.
+    def _frontend(self, rgb_data, depth_data, calib, depth_cut=None):
+        """Everything of tracker.py:75-120 that needs no host decision: intensity, pyramids, gradients, preprocessing
+        (and, when depth_cut = (near, far) is given, the caller's depth clipping of main.py:56-57).
         Returns (Is, Ds, Gs, points (n_max,3), normals (n_max,3), count i32[1]); no host sync."""
+        if depth_cut is not None:
+            depth_data = torch.where((depth_data < depth_cut[0]) | (depth_data > depth_cut[1]),
+                                     torch.full_like(depth_data, float("nan")), depth_data)
         cur_intensity = torch.mean(rgb_data, dim=-1)
         Is, Ds, Gs = self._make_image_pyramid(cur_intensity, depth_data)
         out_p, out_n, cnt = ext.preprocess_frame(Ds[0].contiguous(), calib.fx, calib.fy, calib.cx, calib.cy, 16, 0.05, 16, 0.1,
                                                  (0.0, 0.0, 0.0), 0.02, self.map.div_mode, sync=False)
         return Is, Ds, Gs, out_p, out_n, cnt
 
-    def _frontend_graphed(self, rgb_data, depth_data, calib):
+    def _frontend_graphed(self, rgb_data, depth_data, calib, depth_cut=None):
         """Replays the captured front end on copies of the inputs.  The first call per key runs eagerly (loads kernels,
         sizes workspaces); later calls capture / replay.  Two graphs per key alternate (their outputs are static buffers,
         and the pyramids of frame t are still read as `last_*` while frame t+1 is processed)."""
-        base = (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode)
+        base = (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode,
+                None if depth_cut is None else tuple(depth_cut))
         seen = self._fe_seen.get(base, 0)
         self._fe_seen[base] = seen + 1
         if seen == 0:
-            return self._frontend(rgb_data, depth_data, calib)
+            return self._frontend(rgb_data, depth_data, calib, depth_cut)
         key = base + (seen & 1,)
         ent = self._fe_graphs.get(key)
         if ent is None:
@@ -144,13 +149,13 @@ class SDFTracker:
             side = torch.cuda.Stream(self.map.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                self._frontend(ent["rgb"], ent["depth"], calib)
+                self._frontend(ent["rgb"], ent["depth"], calib, depth_cut)
             cur.wait_stream(side)
             from . import _lib
             before = dict(_lib.CALLS)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                ent["out"] = self._frontend(ent["rgb"], ent["depth"], calib)
+                ent["out"] = self._frontend(ent["rgb"], ent["depth"], calib, depth_cut)
             ent["graph"] = graph
             ent["calls"] = {k: v - before.get(k, 0) for k, v in _lib.CALLS.items() if v != before.get(k, 0)}   # C calls inside one replay
             self._fe_graphs[key] = ent
@@ -161,19 +166,25 @@ class SDFTracker:
             _lib.CALLS[k] = _lib.CALLS.get(k, 0) + v
         return ent["out"]
 
-    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False):
-        """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid."""
+    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False, depth_cut=None):
+        """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid.
+        depth_cut = (near, far), optional: depths outside the range become NaN here (what main.py:56-57 does before the
+        call), so the clipping is part of the captured front end instead of five eager launches."""
         if self.fused_preprocess and self.sdf_args.subsample == 0.5:
             graphed = self.graph_frontend
             fe = self._frontend_graphed if graphed else self._frontend
             with torch.cuda.device(self.map.device):
-                cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib)
+                cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib,
+                                                                            depth_cut)
             m = int(cnt.item())                                   # the one host read of the front end
             if m < 0:
                 raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
             pc_data, normal_data = out_p[:m], out_n[:m]
         else:
             graphed = False
+            if depth_cut is not None:
+                depth_data = torch.where((depth_data < depth_cut[0]) | (depth_data > depth_cut[1]),
+                                         torch.full_like(depth_data, float("nan")), depth_data)
             cur_intensity = torch.mean(rgb_data, dim=-1)
             cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
             pc_data, normal_data = self.preprocess_depth(cur_depth[0], calib)

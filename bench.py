@@ -181,7 +181,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(e2e):
+    def run(e2e, time_kernels=False):
         m, trk = make_system(dfb, dev)
         hg_events = []
         orig = trk.compute_sdf_Hg
@@ -194,7 +194,7 @@ def run_ours(args):
             hg_events.append((a, b, float(trk._hg_host[43]), not no_grad))
             return out
         poses = []
-        trk.time_kernels = True
+        trk.time_kernels = time_kernels
         sampler = ClockSampler(local)                        # NVML is opened here, outside the timed region
         for i in range(Wm):
             l2_flush.zero_()
@@ -253,6 +253,9 @@ def run_ours(args):
 
     res = run(e2e=False)
     res_e2e = run(e2e=True)
+    # third timed region, same K frames: CUDA events around every launch of the dominant kernel (roofline numbers only;
+    # the per-launch event synchronisation costs ~5 % of the frame, so it is kept out of the two throughput passes)
+    res_k = run(e2e=False, time_kernels=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -262,7 +265,7 @@ def run_ours(args):
     pk = peaks()
     value = world * K / (res["ms"] * 1e-3)
     e2e_value = world * K / (res_e2e["ms"] * 1e-3)
-    ach = res["hg_flops"] / max(res["hg_time"], 1e-12) / 1e12
+    ach = res_k["hg_flops"] / max(res_k["hg_time"], 1e-12) / 1e12
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": round(res["ms"] / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,10 +279,12 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(640 * (res_e2e["sdf_evals"] + res_e2e["rgb_evals"]) / n_frames)},
         "gpu_launches": int(res["launches"]),
-        "roofline": {"bound": "tensor", "kernel": "sdf_hg_kernel (tcgen05 FP16 engine: fused decoder fwd+bwd+JtJ reduction)",
+        "roofline": {"bound": "tensor", "kernel": "gn_eval_kernel (tcgen05 FP16 engine: one Gauss-Newton evaluation = decoder fwd+bwd+JtJ over "
+                               "the frame's points, photometric pixels, 6x6 solve; FLOPs counted: decoder only)",
                      "achieved": round(ach, 3), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["bf16_sustained"], 5), "traffic": ncu_traffic(), "peak_source": pk["src"] + " bf16 sustained",
-                     "launches": res["hg_launches"], "avg_launch_us": round(1e6 * res["hg_time"] / max(res["hg_launches"], 1), 1)},
+                     "launches": res_k["hg_launches"], "avg_launch_us": round(1e6 * res_k["hg_time"] / max(res_k["hg_launches"], 1), 1),
+                     "timed_in": "a third pass over the same K frames (events around every launch)"},
     }
     if world == 1:
         line["cpu_baseline"] = cpu_reference(sample_frames=1, quiet=True)

@@ -11,6 +11,7 @@ from . import ext, map, tracker, sharded            # noqa: F401
 from .map import DenseIndexedMap                    # noqa: F401
 from .tracker import SDFTracker, FrameIntrinsic     # noqa: F401
 from .motion import Isometry, Quaternion            # noqa: F401
+from ._lib import DfbError                          # noqa: F401
 
 __all__ = ["ext", "map", "tracker", "motion", "weights", "synth", "sharded", "DenseIndexedMap", "SDFTracker", "FrameIntrinsic",
-           "Isometry", "Quaternion"]
+           "Isometry", "Quaternion", "DfbError"]

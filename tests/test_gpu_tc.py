@@ -151,3 +151,66 @@ def test_tc_encoder_vs_oracle_and_golden(weights, engines):
     rel = np.abs(lat - refl).max() / np.abs(refl).max()
     print("integrate (tcgen05 encoder) latent max err / max|ref| = %.2e" % rel)
     assert rel <= 1e-3          # north-star tolerance; measured 1.8e-4 (the FP32 encoder engine gives 6e-7)
+
+
+def _track3(weights, native, iter_config):
+    from util import TRACKING, ns
+    d = pkg()
+    T = dict(np.load(GOLD / "track_golden.npz"))
+    m = make_map(weights)
+    cfg = dict(TRACKING); cfg["iter_config"] = iter_config
+    trk = d.SDFTracker(m, ns(cfg))
+    trk.native_gn = native
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    first = d.Isometry(q=d.Quaternion(array=d.synth.FIRST_TQ[3:]), t=np.array(d.synth.FIRST_TQ[:3]))
+    out = []
+    for i in range(3):
+        depth = torch.from_numpy(T[f"f{i}_depth_u16"].astype(np.float32)) / 5000.0
+        rgb = torch.from_numpy(T[f"f{i}_rgb_u8"]).float() / 255.
+        depth[torch.logical_or(depth < 0.5, depth > 5.0)] = float("nan")
+        pose = trk.track_camera(rgb.to(DEV).contiguous(), depth.to(DEV).contiguous(), calib, first if i == 0 else None)
+        if i == 0:
+            pc, nrm = trk.last_processed_pc
+            m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+        out.append((pose.q.rotation_matrix.copy(), pose.t.copy()))
+    return out, trk.n_sdf_evals, trk.n_rgb_evals
+
+
+@pytest.mark.parametrize("iter_config", [
+    [{"n": 3, "type": [["rgb", 2]]}, {"n": 3, "type": [["sdf"], ["rgb", 1]]}, {"n": 8, "type": [["sdf"], ["rgb", 0]]}],
+    [{"n": 6, "type": [["sdf"]]}],                                   # SDF term alone: the fused kernel without pixels
+    [{"n": 4, "type": [["rgb", 1]]}, {"n": 4, "type": [["rgb", 0]]}],   # photometric-only groups: pixel kernel + last-block step
+])
+def test_device_resident_gn_equals_python_loop_tc(weights, engines, iter_config):
+    """tcgen05 engine: the one-launch-per-evaluation driver (SDF tiles + work-stolen photometric pixels + last-block step,
+    all state on the device) against the Python loop that calls the two term kernels and solves on the host
+    (tracker.py:225-288).  The sums are added in a different order (1e-7 relative on H, g), which the ill-conditioned
+    low-resolution golden sequence amplifies to ~3e-5 on the pose; the evaluation counts (accept / rollback path) match."""
+    engines.dfb_set_decoder_engine(1)
+    a, b = _track3(weights, True, iter_config), _track3(weights, False, iter_config)
+    print("evaluations (sdf, rgb): native", a[1:], "python loop", b[1:])
+    for (Ra, ta), (Rb, tb) in zip(a[0], b[0]):
+        assert np.abs(Ra - Rb).max() < 1e-4 and np.abs(ta - tb).max() < 1e-4
+    assert abs(a[1] - b[1]) <= 1 and abs(a[2] - b[2]) <= 1          # same accept / rollback path (a knife-edge step may differ)
+
+
+def test_gn_error_paths_tc(weights, engines):
+    """No valid SDF sample: 1/0 scaling -> NaN normal equations -> the driver reports a singular system (tracker.py would
+    raise numpy.linalg.LinAlgError) and leaves the pose untouched; the next call works again."""
+    from util import TRACKING, ns
+    d = pkg()
+    engines.dfb_set_decoder_engine(1)
+    m = make_map(weights)
+    G = dict(np.load(GOLD / "map_golden.npz"))
+    m.integrate_keyframe(torch.from_numpy(G["Pw"]).to(DEV), torch.from_numpy(G["Nw"]).to(DEV))
+    cfg = dict(TRACKING); cfg["iter_config"] = [{"n": 2, "type": [["sdf"]]}]
+    trk = d.SDFTracker(m, ns(cfg))
+    last = d.Isometry.from_matrix(G["hg_last_R"], G["hg_last_t"])
+    trk.all_pd_pose.append(last)
+    far = torch.full((1000, 3), 50.0, device=DEV)                    # outside the map: no valid query
+    for pts in (far, torch.zeros((0, 3), device=DEV)):
+        with pytest.raises(d.DfbError):
+            trk.gauss_newton(last.dot(d.Isometry()), None, None, None, pts, None)
+    good = torch.from_numpy(G["Pc"]).to(DEV)
+    pose = trk.gauss_newton(last.dot(d.Isometry()), None, None, None, good, None)
+    assert np.isfinite(pose.t).all()

@@ -705,6 +705,11 @@ static int grid_for(long long n) { return (int)std::min<long long>(div_up(n, T),
 }  // namespace tc
 
 #ifdef DFB_TC_PROFILE
+extern "C" int dfb_debug_read_step_prof(unsigned long long* h_out) {   // marks of the last step run inside gn_eval_kernel
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h_out, gn::g_step_prof, sizeof(unsigned long long) * 16);
+  return 0;
+}
 extern "C" int dfb_debug_read_prof(unsigned long long* h_out, int* h_n) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h_n, tc::g_prof_n, sizeof(int));

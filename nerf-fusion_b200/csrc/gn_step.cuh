@@ -14,6 +14,13 @@ struct StepArgs {
 };
 constexpr int STEP_SCRATCH_BYTES = 2048;   // shared-memory scratch the step needs (8-byte aligned)
 
+#ifdef DFB_TC_PROFILE
+static __device__ unsigned long long g_step_prof[16];
+#define STEP_MARK(i) do { if ((threadIdx.x & 31) == 0) g_step_prof[i] = clock64(); } while (0)
+#else
+#define STEP_MARK(i) do {} while (0)
+#endif
+
 // All of this runs in one device thread (gn_step_kernel); loops have constant bounds and are unrolled so poses and the
 // 6x7 elimination tableau stay in registers (no local-memory traffic on the critical path between two evaluations).
 struct Pose {   // x -> R x + t, float64
@@ -201,12 +208,14 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
   double* gsv = Hs + 36;
   int* flags = reinterpret_cast<int*>(gsv + 8);
   const int lane = threadIdx.x & 31;
+  STEP_MARK(0);
   {
     const double* src = reinterpret_cast<const double*>(gs);
     double* dst = reinterpret_cast<double*>(&sh);
     for (int i = lane; i < ND; i += 32) dst[i] = __ldcg(src + i);      // L2: the sums were produced by atomics of other blocks
   }
   __syncwarp();
+  STEP_MARK(1);
   const int gi = a.gi;
   const bool run = !sh.done[gi];
   const bool no_grad = (a.step == a.n_it);
@@ -232,6 +241,7 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
       }
     }
     __syncwarp();
+    STEP_MARK(2);
     if (lane == 0) {
       double energy = 0.0;
       if (a.use_sdf) energy += sh.sums[0][27] * scale0;
@@ -249,7 +259,9 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
         sh.last_energy = energy;
         if (!no_grad) {
           double xi[6];
-          if (!solve6(Hs, gsv, xi)) {
+          const bool solved = solve6(Hs, gsv, xi);
+          STEP_MARK(3);
+          if (!solved) {
             sh.error = 1;
 #pragma unroll
             for (int i = 0; i < 8; ++i) sh.done[i] = 1;
@@ -265,12 +277,14 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
             for (int i = 0; i < 9; ++i) sh.delta[i] = nd.R[i];
 #pragma unroll
             for (int i = 0; i < 3; ++i) sh.delta[9 + i] = nd.t[i];
+            STEP_MARK(4);
           }
         } else {
           sh.done[gi] = 1;                                            // the evaluation-only pass closes the group
         }
       }
       publish_pose(&sh);
+      STEP_MARK(5);
       flags[1] = broke;
     }
     __syncwarp();
@@ -283,7 +297,9 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
     const double* src = reinterpret_cast<const double*>(&sh);
     for (int i = lane; i < ND; i += 32) dst[i] = src[i];
   }
+  STEP_MARK(6);
   write_record(a.ring + (a.seq & 3), a.seq, sh.delta, run ? 1 : 0, flags[1], sh.error, cnt0, cnt1);
+  STEP_MARK(7);
 }
 
 // Tail of a term kernel: the last block of the grid to arrive runs the step (classic threadfence reduction).  Every

@@ -30,3 +30,11 @@ for i, v in enumerate(t[:len(names)]):
     if "fwd" in nm or "bwd" in nm or "heads" in nm or "lookup" in nm:
         prev = v; continue
     print(f"{i:3d} {nm:28s} +{int(v - prev):6d}  @{int(v - t0):7d} cycles"); prev = v
+
+sb = (C.c_ulonglong * 16)()
+raw.dfb_debug_read_step_prof(sb)
+st = np.array(list(sb)[:8], dtype=np.int64)
+lab = ["enter", "state loaded", "H,g scaled", "solved", "pose updated", "pose published", "state stored", "record written"]
+print("step (last block of the last launch):")
+for i in range(1, 8):
+    print(f"   {lab[i]:16s} +{int(st[i] - st[i - 1]):6d} cycles")

@@ -196,6 +196,8 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
  * terms, solves the 6x6 system and updates the pose in float64, rolls a step back when its energy rises (which ends the
  * group, tracker.py:269-271) and publishes the pose of the next evaluation, so nothing is read back between
  * iterations; the host keeps one evaluation of look-ahead queued and only polls a 128-byte record per step.
+ * obs_xyz holds n rows; if d_n (device int32, may be NULL) is given, only the first min(n, max(*d_n, 0)) rows are used, so
+ * the caller need not read the row count of dfb_preprocess_frame back before queueing the solve.
  * Poses are 12 doubles: R row-major (9) then t (3).  h_delta_pose is in/out (initial guess -> result; untouched on error).
  * d_scratch: device, DFB_GN_SCRATCH_DOUBLES doubles.  h_pinned: PINNED (device-visible) host memory,
  * DFB_GN_PINNED_DOUBLES doubles.
@@ -218,7 +220,7 @@ typedef struct {
   const float* prev_I; const float* prev_D; const float* cur_I; const float* cur_D; const float* cur_G;
   int32_t H, W;
 } dfb_rgb_level;
-int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n,
+int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n, const int32_t* d_n,
                      const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
                      const float* decoder_blob, const dfb_rgb_level* h_levels, const double* h_intr,
                      const double* h_last_pose, double* h_delta_pose, double* d_scratch, double* h_pinned,

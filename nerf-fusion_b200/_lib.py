@@ -75,7 +75,7 @@ SIGNATURES = {
     "dfb_decoder_forward": (_I, [_P, _I, _P, _P, _P, _P]),
     "dfb_get_sdf": (_I, [_MP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dfb_sdf_hg": (_I, [_MP, _P, _I, _FP, _P, _P, _P, _P, _I, _F, _I, _P, _P]),
-    "dfb_gauss_newton": (_I, [_MP, C.POINTER(GnConfig), _P, _I, _P, _P, _P, _P, C.POINTER(RgbLevel), C.POINTER(C.c_double),
+    "dfb_gauss_newton": (_I, [_MP, C.POINTER(GnConfig), _P, _I, _P, _P, _P, _P, _P, C.POINTER(RgbLevel), C.POINTER(C.c_double),
                               C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.POINTER(C.c_int32), _P]),
     "dfb_decode_cubes_ws_bytes": (_SZ, [_I, _I]),
     "dfb_decode_cubes": (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),

@@ -177,14 +177,14 @@ struct GnShared {
   int rgb_cursor;            // next chunk of photometric pixels (work stealing inside the fused evaluation kernel)
   int pad_;
 };
-int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int32_t* n_dev, const int64_t* indexer, const float* latent_vecs,
                      const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
                      cudaStream_t s);                                                                        // decoder.cu
 int launch_rgb_hg_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
                      int compute_J, GnShared* gs, int gi, cudaStream_t s);                                   // photometric.cu
 namespace gn { struct StepArgs; }
 // fused evaluation (tcgen05 engine): SDF term + optional photometric term (L may be null) + step, one launch      // decoder.cu / decoder_tc.cu
-int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int32_t* n_dev, const int64_t* indexer, const float* latent_vecs,
                       const float* voxel_obs_count, const float* decoder_blob, int sdf_robust, float sdf_robust_k, int compute_J,
                       const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int rgb_robust,
                       float rgb_robust_k, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s);

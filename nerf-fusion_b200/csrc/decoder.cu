@@ -95,11 +95,12 @@ __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
                                                           const int64_t* __restrict__ indexer, const float* __restrict__ latents,
                                                           const float* __restrict__ obs_count, const float* __restrict__ blob,
                                                           int robust, float robust_k, int with_J, double* __restrict__ packed,
-                                                          const GnShared* __restrict__ gs, int gi) {
+                                                          const GnShared* __restrict__ gs, int gi, const int* __restrict__ n_dev) {
   if (gs) {
     if (gs->done[gi]) return;
     P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
   }
+  if (n_dev) n = min(n, max(*n_dev, 0));
   DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
   decoder_load_small(S, blob);
   const int tid = threadIdx.x;
@@ -327,7 +328,7 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
   int rc = set_dec_smem(sdf_hg_kernel);
   if (rc) return rc;
   sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count,
-                                                            decoder_blob, robust, robust_k, compute_J, packed, nullptr, 0);
+                                                            decoder_blob, robust, robust_k, compute_J, packed, nullptr, 0, nullptr);
   launch_hg_expand(packed, out44, s);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
@@ -388,7 +389,7 @@ int dfb_decode_cubes(const float* latent_vecs, const int64_t* occ, int B, int r,
 // Gauss-Newton evaluations launched by gauss_newton.cu.
 namespace dfb {
 // tcgen05 engine: SDF term + optional photometric term + step in one launch (decoder_tc.cu gn_eval_kernel)
-int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int32_t* n_dev, const int64_t* indexer, const float* latent_vecs,
                       const float* voxel_obs_count, const float* decoder_blob, int sdf_robust, float sdf_robust_k, int compute_J,
                       const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int rgb_robust,
                       float rgb_robust_k, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s) {
@@ -399,12 +400,12 @@ int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int 
     R.P.min_grad_scale = min_grad_scale; R.P.max_depth_delta = max_depth_delta;
     R.robust = rgb_robust; R.robust_k = rgb_robust_k; R.on = 1;
   }
-  return tc_gn_eval(to_dev(h_params), obs_xyz, n, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), sdf_robust, sdf_robust_k,
+  return tc_gn_eval(to_dev(h_params), obs_xyz, n, n_dev, indexer, latent_vecs, voxel_obs_count, tc_part(decoder_blob), sdf_robust, sdf_robust_k,
                     compute_J, R, gs, gi, *sa, s);
 }
 
 // FP32 CUDA-core engine: the SDF term alone (pose and "group finished" flag from `gs`, sums into gs->sums[0])
-int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int64_t* indexer, const float* latent_vecs,
+int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n, const int32_t* n_dev, const int64_t* indexer, const float* latent_vecs,
                      const float* voxel_obs_count, const float* decoder_blob, int robust, float robust_k, int compute_J, GnShared* gs, int gi,
                      cudaStream_t s) {
   if (n == 0) return DFB_OK;
@@ -412,7 +413,7 @@ int launch_sdf_hg_gn(const dfb_map_params* h_params, const float* obs_xyz, int n
   int rc = set_dec_smem(sdf_hg_kernel);
   if (rc) return rc;
   sdf_hg_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), s>>>(to_dev(h_params), P, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob,
-                                                            robust, robust_k, compute_J, gs->sums[0], gs, gi);
+                                                            robust, robust_k, compute_J, gs->sums[0], gs, gi, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -92,7 +92,7 @@ int tc_sdf_hg(const MapDev& M, const PoseDev& P, const float* obs, int n, const 
               const float* obs_count, const void* blob, int robust, float robust_k, int with_J, double* packed, cudaStream_t s);
 struct RgbDev;
 namespace gn { struct StepArgs; }
-int tc_gn_eval(const MapDev& M, const float* obs, int n, const int64_t* indexer, const float* latents, const float* obs_count,
+int tc_gn_eval(const MapDev& M, const float* obs, int n, const int* n_dev, const int64_t* indexer, const float* latents, const float* obs_count,
                const void* blob, int robust, float robust_k, int with_J, const RgbDev& R, GnShared* gs, int gi, const gn::StepArgs& sa,
                cudaStream_t s);
 int tc_cube_low(const float* latents, const int64_t* occ, int B, int r, float vsize, float a, const void* tc_blob, float* low_sdf,

@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
 // have, and their SM's tensor pipe is busy with the sibling group anyway); both terms' sums go to GnShared with one
 // atomic per value per block; the last block to finish runs the step (solve, pose update, record for the host).
 constexpr int RGB_PIX = 2;                       // pixels per thread per chunk (chunk = GT * RGB_PIX pixels)
-__global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float* __restrict__ obs, int n, const int64_t* __restrict__ indexer,
+__global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float* __restrict__ obs, int n, const int* __restrict__ n_dev,
+                                                       const int64_t* __restrict__ indexer,
                                                        const float* __restrict__ latents, const float* __restrict__ obs_count,
                                                        const void* __restrict__ blob, int robust, float robust_k, int with_J, RgbDev R,
                                                        GnShared* gs, int gi, gn::StepArgs sa) {
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
     return;
   }
   const PoseDev P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
+  if (n_dev) n = min(n, max(*n_dev, 0));         // row count still on the device (dfb_preprocess_frame's output)
   Ctx c;
 #ifdef DFB_TC_PROFILE
   c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
@@ -739,13 +741,13 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
   return DFB_OK;
 }
 
-int tc_gn_eval(const MapDev& M, const float* obs, int n, const int64_t* indexer, const float* latents, const float* obs_count,
+int tc_gn_eval(const MapDev& M, const float* obs, int n, const int* n_dev, const int64_t* indexer, const float* latents, const float* obs_count,
                const void* blob, int robust, float robust_k, int with_J, const RgbDev& R, GnShared* gs, int gi, const gn::StepArgs& sa,
                cudaStream_t s) {
   int rc = tc::prep(tc::gn_eval_kernel);
   if (rc) return rc;
   const int grid = R.on ? sm_count() : std::max(1, tc::grid_for(n));     // every SM takes photometric chunks
-  tc::gn_eval_kernel<<<grid, tc::CTA_T, tc::SM_ALLOC, s>>>(M, obs, n, indexer, latents, obs_count, blob, robust, robust_k, with_J, R, gs, gi, sa);
+  tc::gn_eval_kernel<<<grid, tc::CTA_T, tc::SM_ALLOC, s>>>(M, obs, n, n_dev, indexer, latents, obs_count, blob, robust, robust_k, with_J, R, gs, gi, sa);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32) gn_step_kernel(dfb::GnShared* gs, StepArgs
 }  // namespace
 
 extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_config* h_cfg, const float* obs_xyz, int n,
-                                const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
+                                const int32_t* d_n, const int64_t* indexer, const float* latent_vecs, const float* voxel_obs_count,
                                 const float* decoder_blob, const dfb_rgb_level* h_levels, const double* h_intr,
                                 const double* h_last_pose, double* h_delta_pose, double* d_scratch, double* h_pinned,
                                 int32_t* h_stats, void* stream) {
@@ -97,7 +97,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
       // ONE launch per evaluation: SDF tiles on the tensor cores, photometric pixels work-stolen by idle tile groups,
       // and the step as the tail of the last block (decoder_tc.cu)
       if (timing) { out.sdf_event = n_events; cudaEventRecord(event(2 * n_events), s); }
-      int rc = dfb::launch_sdf_rgb_gn(h_params, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
+      int rc = dfb::launch_sdf_rgb_gn(h_params, obs_xyz, n, d_n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
                                       h_cfg->sdf_robust_k, no_grad ? 0 : 1, use_rgb ? &h_levels[lvl] : nullptr, intr4,
                                       h_cfg->rgb_min_grad_scale, h_cfg->rgb_max_depth_delta, h_cfg->rgb_robust, h_cfg->rgb_robust_k, gs, gi,
                                       &sa, s);
@@ -114,7 +114,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     n_launches += (use_sdf && n > 0 ? 1 : 0) + use_rgb + 1;
     if (use_sdf) {                               // FP32 CUDA-core engine: term kernels, then the stand-alone step kernel
       if (timing) { out.sdf_event = n_events; cudaEventRecord(event(2 * n_events), s); }
-      int rc = dfb::launch_sdf_hg_gn(h_params, obs_xyz, n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
+      int rc = dfb::launch_sdf_hg_gn(h_params, obs_xyz, n, d_n, indexer, latent_vecs, voxel_obs_count, decoder_blob, h_cfg->sdf_robust,
                                      h_cfg->sdf_robust_k, no_grad ? 0 : 1, gs, gi, s);
       if (rc) return rc;
       if (timing) { cudaEventRecord(event(2 * n_events + 1), s); ++n_events; }

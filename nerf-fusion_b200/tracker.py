@@ -176,12 +176,26 @@ class SDFTracker:
             with torch.cuda.device(self.map.device):
                 cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib,
                                                                             depth_cut)
-            m = int(cnt.item())                                   # the one host read of the front end
-            if m < 0:
-                raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
+            # The row count stays on the device while the pose solve is queued behind the front end (the kernels read it
+            # there); it is read back once the solve has returned.
+            defer = self.native_gn and set_pose is None and not for_pc and len(self.all_pd_pose) > 0
+            final_pose = None
+            if defer:
+                try:
+                    final_pose = self.gauss_newton(self.all_pd_pose[-1].dot(Isometry()), cur_intensity, cur_depth, cur_dIdxy, out_p, calib,
+                                                   obs_count=cnt)
+                finally:
+                    m = int(cnt.item())
+                    if m < 0:
+                        raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
+            else:
+                m = int(cnt.item())                               # the one host read of the front end
+                if m < 0:
+                    raise RuntimeError("preprocess_frame: box-filter key range exceeds the bitmap capacity")
             pc_data, normal_data = out_p[:m], out_n[:m]
         else:
             graphed = False
+            final_pose = None
             if depth_cut is not None:
                 depth_data = torch.where((depth_data < depth_cut[0]) | (depth_data > depth_cut[1]),
                                          torch.full_like(depth_data, float("nan")), depth_data)
@@ -194,7 +208,7 @@ class SDFTracker:
             return self.last_processed_pc
         if set_pose is not None:
             final_pose = set_pose
-        else:
+        elif final_pose is None:
             assert len(self.all_pd_pose) > 0
             final_pose = self.gauss_newton(self.all_pd_pose[-1].dot(Isometry()), cur_intensity, cur_depth, cur_dIdxy, pc_data, calib)
         self.last_intensity = cur_intensity
@@ -248,7 +262,7 @@ class SDFTracker:
         return H * error_scale, g * error_scale, float(e * error_scale)
 
     # ------------------------------------------------------------------------------------------ Gauss-Newton
-    def _gauss_newton_native(self, last_pose, delta_pose, Is, Ds, Gs, obs_xyz, calib):
+    def _gauss_newton_native(self, last_pose, delta_pose, Is, Ds, Gs, obs_xyz, calib, obs_count=None):
         from . import _lib
         from ._lib import GnConfig, RgbLevel
         m = self.map
@@ -287,7 +301,8 @@ class SDFTracker:
             stats[4] = 0x54494d45
         obs = obs_xyz.contiguous()
         with torch.cuda.device(m.device):
-            check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0), _p(m.indexer), _p(m.latent_vecs),
+            check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0),
+                                         _p(obs_count) if obs_count is not None else None, _p(m.indexer), _p(m.latent_vecs),
                                          _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._gn_dev),
                                          C.c_void_p(self._gn_pinned.data_ptr()), stats, _stream()))
         self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
@@ -302,14 +317,16 @@ class SDFTracker:
                 self.rgb_args.weight = max(self.rgb_args.weight, 500.)
         return last_pose.dot(new_delta)
 
-    def gauss_newton(self, init_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz, calib):
+    def gauss_newton(self, init_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz, calib, obs_count=None):
         """tracker.py:225-288 (control flow unchanged: rollback+break when the energy rises, one evaluation-only pass per
         group, instability counter)."""
         last_pose = self.all_pd_pose[-1]
         cur_delta_pose = last_pose.inv().dot(init_pose)
         if self.native_gn:
             return self._gauss_newton_native(last_pose, cur_delta_pose, cur_intensity_pyramid, cur_depth_pyramid,
-                                             cur_dIdxy_pyramid, obs_xyz, calib)
+                                             cur_dIdxy_pyramid, obs_xyz, calib, obs_count)
+        if obs_count is not None:
+            obs_xyz = obs_xyz[:int(obs_count.item())]
         last_delta_pose = copy.deepcopy(cur_delta_pose)
         i_iter = 0
         for group in self.args.iter_config:

@@ -191,11 +191,16 @@ int launch_sdf_rgb_gn(const dfb_map_params* h_params, const float* obs_xyz, int 
 // photometric term + step, one launch                                                                                // photometric.cu
 int launch_rgb_step_gn(const dfb_rgb_level* L, const float* intr4, float min_grad_scale, float max_depth_delta, int robust, float robust_k,
                        int compute_J, GnShared* gs, int gi, const gn::StepArgs* sa, cudaStream_t s);
-struct GnRecord {            // written by the step kernel into pinned host memory, polled by the driver
-  int seq;                   // written last (after a system-wide fence)
-  int executed, broke, error;
-  double cnt[2];             // valid counts of the two terms
-  double delta[12];          // pose after this step
+// Written by the step into pinned host memory, polled by the driver.  The first 16 bytes go out as ONE vector store
+// (seq and check bracket the payload, so the host accepts the header only when both 8-byte halves have landed); delta is
+// written -- and fenced system-wide -- before the header, and only by the step that ends its group (GN_HAS_DELTA).
+struct alignas(16) GnRecord {
+  int seq;                   // sequence number of the evaluation
+  int flags;                 // GN_EXECUTED | GN_BROKE | GN_ERROR | GN_HAS_DELTA
+  float cnt0;                // valid count of the SDF term (exact below 2^24)
+  int check;                 // seq ^ GN_CHECK
+  double delta[12];          // pose after this step (valid when GN_HAS_DELTA)
 };
+constexpr int GN_EXECUTED = 1, GN_BROKE = 2, GN_ERROR = 4, GN_HAS_DELTA = 8, GN_CHECK = 0x5a5a5a5a;
 
 }  // namespace dfb

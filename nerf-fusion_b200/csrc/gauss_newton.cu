@@ -61,7 +61,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
   GnRecord* ring = nullptr;                                        // device view of the pinned ring
   DFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ring), h_pinned, 0));
   volatile GnRecord* hring = reinterpret_cast<volatile GnRecord*>(h_pinned);
-  for (int i = 0; i < 4; ++i) hring[i].seq = 0;
+  for (int i = 0; i < 4; ++i) { hring[i].seq = 0; hring[i].check = 0; }
 
   static std::vector<cudaEvent_t> events;                           // pairs, grown on demand (timing only)
   auto event = [&](size_t i) -> cudaEvent_t {
@@ -129,11 +129,12 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     return DFB_OK;
   };
   // wait for the record of a slot (spin on pinned memory; the stream is polled for errors now and then)
-  auto wait = [&](const Slot& sl, GnRecord& r) -> int {
+  struct Rec { bool executed, broke, error, has_delta; double cnt0; double delta[12]; };
+  auto wait = [&](const Slot& sl, Rec& r) -> int {
     volatile GnRecord* rec = hring + (sl.seq & 3);
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spin = 0;; ++spin) {
-      if (rec->seq == sl.seq) { __atomic_thread_fence(__ATOMIC_ACQUIRE); break; }
+      if (rec->seq == sl.seq && rec->check == (sl.seq ^ dfb::GN_CHECK)) { __atomic_thread_fence(__ATOMIC_ACQUIRE); break; }
       if ((spin & 0xfff) == 0xfff) {
         cudaError_t e = cudaStreamQuery(s);
         if (e != cudaSuccess && e != cudaErrorNotReady) { dfb::set_error("gauss_newton: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
@@ -143,12 +144,16 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
         if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) { dfb::set_error("gauss_newton: timed out waiting for the device"); return DFB_E_CUDA; }
       }
     }
-    r.executed = rec->executed; r.broke = rec->broke; r.error = rec->error;
-    r.cnt[0] = rec->cnt[0]; r.cnt[1] = rec->cnt[1];
-    for (int i = 0; i < 12; ++i) r.delta[i] = rec->delta[i];
+    const int flags = rec->flags;
+    r.executed = flags & dfb::GN_EXECUTED; r.broke = flags & dfb::GN_BROKE; r.error = flags & dfb::GN_ERROR;
+    r.has_delta = flags & dfb::GN_HAS_DELTA;
+    r.cnt0 = (double)rec->cnt0;
+    if (r.has_delta)
+      for (int i = 0; i < 12; ++i) r.delta[i] = rec->delta[i];
     return DFB_OK;
   };
-  auto account = [&](const Slot& sl, const GnRecord& r) {
+  auto account = [&](const Slot& sl, const Rec& r) {
+    if (r.error) error = 1;
     if (!r.executed) return;
     const int n_it = h_cfg->n_iter[sl.gi];
     const bool no_grad = (sl.step == n_it);
@@ -160,12 +165,11 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
         cudaEventSynchronize(event(2 * sl.sdf_event + 1));   // the record is written by the kernel's last block, just before it exits
         cudaEventElapsedTime(&ms, event(2 * sl.sdf_event), event(2 * sl.sdf_event + 1));
         sdf_ms += ms;
-        (no_grad ? sdf_q_nj : sdf_q_j) += r.cnt[0];
+        (no_grad ? sdf_q_nj : sdf_q_j) += r.cnt0;
       }
     }
     if (h_cfg->rgb_level[sl.gi] >= 0) ++n_rgb;
-    memcpy(delta_out, r.delta, sizeof(delta_out));
-    if (r.error) error = 1;
+    if (r.has_delta) memcpy(delta_out, r.delta, sizeof(delta_out));   // the step that ends a group carries the pose
   };
 
   int rc = DFB_OK;
@@ -183,7 +187,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
         if (rc) break;
         have_next = true;
       }
-      GnRecord r;
+      Rec r;
       rc = wait(cur, r);
       if (rc) break;
       account(cur, r);

@@ -50,23 +50,25 @@ __device__ __forceinline__ Pose compose(const Pose& a, const Pose& b) {   // a o
 // The reference stores rotations as unit quaternions (pyquaternion normalises on every rotation_matrix access), which
 // re-orthonormalises the pose each iteration; do the same round trip.
 __device__ __forceinline__ void renormalise(double* R) {
+  // matrix -> quaternion -> unit quaternion -> matrix; divisions by a common value are one reciprocal and multiplies
+  // (the step sits between two evaluations: its latency is paid once per Gauss-Newton iteration)
   double q0, q1, q2, q3;
   const double tr = R[0] + R[4] + R[8];
   if (tr > 0) {
-    const double s = sqrt(tr + 1.0) * 2;
-    q0 = 0.25 * s; q1 = (R[7] - R[5]) / s; q2 = (R[2] - R[6]) / s; q3 = (R[3] - R[1]) / s;
+    const double s = sqrt(tr + 1.0) * 2, is = 1.0 / s;
+    q0 = 0.25 * s; q1 = (R[7] - R[5]) * is; q2 = (R[2] - R[6]) * is; q3 = (R[3] - R[1]) * is;
   } else if (R[0] > R[4] && R[0] > R[8]) {
-    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
-    q0 = (R[7] - R[5]) / s; q1 = 0.25 * s; q2 = (R[1] + R[3]) / s; q3 = (R[2] + R[6]) / s;
+    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2, is = 1.0 / s;
+    q0 = (R[7] - R[5]) * is; q1 = 0.25 * s; q2 = (R[1] + R[3]) * is; q3 = (R[2] + R[6]) * is;
   } else if (R[4] > R[8]) {
-    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
-    q0 = (R[2] - R[6]) / s; q1 = (R[1] + R[3]) / s; q2 = 0.25 * s; q3 = (R[5] + R[7]) / s;
+    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2, is = 1.0 / s;
+    q0 = (R[2] - R[6]) * is; q1 = (R[1] + R[3]) * is; q2 = 0.25 * s; q3 = (R[5] + R[7]) * is;
   } else {
-    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
-    q0 = (R[3] - R[1]) / s; q1 = (R[2] + R[6]) / s; q2 = (R[5] + R[7]) / s; q3 = 0.25 * s;
+    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2, is = 1.0 / s;
+    q0 = (R[3] - R[1]) * is; q1 = (R[2] + R[6]) * is; q2 = (R[5] + R[7]) * is; q3 = 0.25 * s;
   }
-  const double n = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-  const double w = q0 / n, x = q1 / n, y = q2 / n, z = q3 / n;
+  const double in = rsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+  const double w = q0 * in, x = q1 * in, y = q2 * in, z = q3 * in;
   R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
   R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
   R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
@@ -83,7 +85,8 @@ __device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.
 #pragma unroll
     for (int i = 0; i < 9; ++i) { p.R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Wd[i]; J[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Wd[i]; }
   } else {
-    const double ax[3] = {phi[0] / angle, phi[1] / angle, phi[2] / angle};
+    const double ia = 1.0 / angle;
+    const double ax[3] = {phi[0] * ia, phi[1] * ia, phi[2] * ia};
     double s, c;
     sincos(angle, &s, &c);
     const double Wa[9] = {0, -ax[2], ax[1], ax[2], 0, -ax[0], -ax[1], ax[0], 0};
@@ -93,7 +96,7 @@ __device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.
       for (int j = 0; j < 3; ++j) {
         const double I = (i == j) ? 1.0 : 0.0, oo = ax[i] * ax[j];
         p.R[3 * i + j] = c * I + (1 - c) * oo + s * Wa[3 * i + j];
-        J[3 * i + j] = (s / angle) * I + (1 - s / angle) * oo + ((1 - c) / angle) * Wa[3 * i + j];
+        J[3 * i + j] = (s * ia) * I + (1 - s * ia) * oo + ((1 - c) * ia) * Wa[3 * i + j];
       }
   }
   renormalise(p.R);
@@ -101,46 +104,50 @@ __device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.
   return p;
 }
 
-// np.linalg.solve(H, -g): LU with partial pivoting, float64.  Returns false when singular / non-finite.
-__device__ __forceinline__ bool solve6(const double* H, const double* g, double* x) {
-  double A[42];
+// np.linalg.solve(H, -g): LU with partial pivoting, float64, by one warp.  Lane j < 7 holds column j of the 6 x 7 tableau
+// [H | -g] in six registers (lanes 7.. shadow lane 6); the pivot choice and the five row factors of a column come from
+// lane c by shuffle, every lane updates its own column.  Same operations per element as the sequential elimination;
+// the solution ends up on every lane.  Returns false when singular / non-finite.
+__device__ __forceinline__ bool solve6_warp(const double* H, const double* g, double* x) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int j = lane < 7 ? lane : 6;
+  double a[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) A[7 * (i) + (j)] = H[6 * i + j];
-    A[7 * (i) + (6)] = -g[i];
-  }
+  for (int r = 0; r < 6; ++r) a[r] = (j < 6) ? H[6 * r + j] : -g[r];
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     int piv = c;
-    double best = fabs(A[7 * (c) + (c)]);
+    double best = fabs(a[c]);
 #pragma unroll
     for (int r = c + 1; r < 6; ++r) {
-      const double v = fabs(A[7 * (r) + (c)]);
+      const double v = fabs(a[r]);
       if (v > best) { best = v; piv = r; }
     }
+    piv = __shfl_sync(FULL, piv, c);
+    best = __shfl_sync(FULL, best, c);
     if (!(best > 0.0)) ok = false;
 #pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      if (piv == r) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) { const double t = A[7 * (c) + (j)]; A[7 * (c) + (j)] = A[7 * (r) + (j)]; A[7 * (r) + (j)] = t; }
-      }
+    for (int r = c + 1; r < 6; ++r) {                    // swap rows c and piv: selects on registers, no indexing
+      const bool sw = (piv == r);
+      const double ac = a[c], ar = a[r];
+      a[c] = sw ? ar : ac;
+      a[r] = sw ? ac : ar;
     }
+    const double pc = __shfl_sync(FULL, a[c], c);
 #pragma unroll
     for (int r = c + 1; r < 6; ++r) {
-      const double f = A[7 * (r) + (c)] / A[7 * (c) + (c)];
-#pragma unroll
-      for (int j = c; j < 7; ++j) A[7 * (r) + (j)] -= f * A[7 * (c) + (j)];
+      const double f = __shfl_sync(FULL, a[r], c) / pc;
+      a[r] -= f * a[c];
     }
   }
 #pragma unroll
   for (int r = 5; r >= 0; --r) {
-    double sacc = A[7 * (r) + (6)];
+    double sacc = __shfl_sync(FULL, a[r], 6);
 #pragma unroll
-    for (int j = r + 1; j < 6; ++j) sacc -= A[7 * (r) + (j)] * x[j];
-    x[r] = sacc / A[7 * (r) + (r)];
+    for (int jj = r + 1; jj < 6; ++jj) sacc -= __shfl_sync(FULL, a[r], jj) * x[jj];
+    x[r] = sacc / __shfl_sync(FULL, a[r], r);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -173,25 +180,24 @@ __device__ __forceinline__ void publish_pose(GnShared* gs) {
 }
 
 
-// record for the host (pinned memory): payload from several lanes, a system-wide fence, then the sequence number
-__device__ __forceinline__ void write_record(GnRecord* rec, int seq, const double* delta, int executed, int broke, int error, double cnt0,
-                                             double cnt1) {
+// Record for the host (pinned memory).  When the step ends its group the pose goes out first and is fenced system-wide;
+// the 16-byte header is one vector store (see GnRecord).
+__device__ __forceinline__ void write_record(GnRecord* rec, int seq, const double* delta, int flags, double cnt0) {
   const int lane = threadIdx.x & 31;
-  if (lane < 12) rec->delta[lane] = delta[lane];
-  if (lane == 12) { rec->executed = executed; rec->broke = broke; rec->error = error; }
-  if (lane == 13) { rec->cnt[0] = cnt0; rec->cnt[1] = cnt1; }
-  __threadfence_system();                        // every lane: its payload stores are visible system-wide ...
-  __syncwarp();                                  // ... before lane 0 publishes the sequence number
-  if (lane == 0) *reinterpret_cast<volatile int*>(&rec->seq) = seq;
+  if (flags & GN_HAS_DELTA) {
+    if (lane < 12) rec->delta[lane] = delta[lane];
+    __threadfence_system();
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const int c0 = __float_as_int((float)cnt0), chk = seq ^ GN_CHECK;
+    asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(rec), "r"(seq), "r"(flags), "r"(c0), "r"(chk) : "memory");
+  }
 }
 
 // A launch of a finished group still owes the host its record (one warp).
 __device__ __forceinline__ void skip_record(const GnShared* gs, const StepArgs& a) {
-  const int lane = threadIdx.x & 31;
-  __shared__ double d[12];
-  if (lane < 12) d[lane] = gs->delta[lane];
-  __syncwarp();
-  write_record(a.ring + (a.seq & 3), a.seq, d, 0, 0, gs->error, 0.0, 0.0);
+  write_record(a.ring + (a.seq & 3), a.seq, nullptr, gs->error ? GN_ERROR : 0, 0.0);
 }
 
 // One Gauss-Newton step for group a.gi, iteration a.step (a.step == a.n_it is the evaluation-only pass, i_iter = -1).
@@ -242,13 +248,20 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
     }
     __syncwarp();
     STEP_MARK(2);
+    // decision (uniform over the warp: every lane reads the same shared values)
+    double energy = 0.0;
+    if (a.use_sdf) energy += sh.sums[0][27] * scale0;
+    if (a.use_rgb) energy += sh.sums[1][27] * scale1;
+    const double last_energy = a.step == 0 ? CUDART_INF : sh.last_energy;
+    const bool rollback = energy > last_energy;                     // tracker.py:269-271: roll back, leave the group
+    double xi[6];
+    bool solved = true;
+    if (!rollback && !no_grad) solved = solve6_warp(Hs, gsv, xi);   // all lanes
+    STEP_MARK(3);
+    __syncwarp();
     if (lane == 0) {
-      double energy = 0.0;
-      if (a.use_sdf) energy += sh.sums[0][27] * scale0;
-      if (a.use_rgb) energy += sh.sums[1][27] * scale1;
       int broke = 0;
-      const double last_energy = a.step == 0 ? CUDART_INF : sh.last_energy;
-      if (energy > last_energy) {                                     // tracker.py:269-271: roll back, leave the group
+      if (rollback) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) sh.delta[i] = sh.last_delta[i];
         sh.done[gi] = 1;
@@ -258,9 +271,6 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
         for (int i = 0; i < 12; ++i) sh.last_delta[i] = sh.delta[i];
         sh.last_energy = energy;
         if (!no_grad) {
-          double xi[6];
-          const bool solved = solve6(Hs, gsv, xi);
-          STEP_MARK(3);
           if (!solved) {
             sh.error = 1;
 #pragma unroll
@@ -298,7 +308,9 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
     for (int i = lane; i < ND; i += 32) dst[i] = src[i];
   }
   STEP_MARK(6);
-  write_record(a.ring + (a.seq & 3), a.seq, sh.delta, run ? 1 : 0, flags[1], sh.error, cnt0, cnt1);
+  const int rflags = (run ? GN_EXECUTED : 0) | (flags[1] ? GN_BROKE : 0) | (sh.error ? GN_ERROR : 0) |
+                     ((run && sh.done[gi]) ? GN_HAS_DELTA : 0);        // the step that ends its group carries the pose
+  write_record(a.ring + (a.seq & 3), a.seq, sh.delta, rflags, cnt0);
   STEP_MARK(7);
 }
 

@@ -40,7 +40,7 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
     capture of this same command (profiles/); None when absent."""
     import csv
-    f = ROOT / "profiles" / "r01_sdf_hg_tc_final_ncu_raw.csv"
+    f = ROOT / "profiles" / "r01_gn_eval_ncu_raw.csv"
     if not f.exists():
         return None
     try:

@@ -197,6 +197,15 @@ def run_ours(args):
             hg_events.append((a, b, float(trk._hg_host[43]), not no_grad))
             return out
         poses = []
+        copy_stream = torch.cuda.Stream(dev)
+
+        def upload(i):
+            """H2D of frame i's depth + colour from pinned memory on the copy stream (double-buffered: issued while the
+            previous frame is being processed, like frames arriving from a camera)."""
+            with torch.cuda.stream(copy_stream):
+                d_ = host_frames[i][0].to(dev, non_blocking=True); c_ = host_frames[i][1].to(dev, non_blocking=True)
+                ev_ = torch.cuda.Event(); ev_.record(copy_stream)
+            return d_, c_, ev_
         trk.time_kernels = time_kernels
         sampler = ClockSampler(local)                        # NVML is opened here, outside the timed region
         for i in range(Wm):
@@ -214,10 +223,15 @@ def run_ours(args):
         marks = []
         t0.record()
         with sampler as cs:
+            nxt = upload(Wm) if e2e else None                                     # inside the timed region
             for i in range(Wm, n_frames):
                 l2_flush.zero_()                                                  # cold L2 for every frame
                 if e2e:
-                    d, c = (t.to(dev, non_blocking=True) for t in host_frames[i])
+                    d, c, ev_up = nxt
+                    nxt = upload(i + 1) if i + 1 < n_frames else None             # next frame's copy overlaps this frame's work
+                    cur_stream = torch.cuda.current_stream()
+                    cur_stream.wait_event(ev_up)
+                    d.record_stream(cur_stream); c.record_stream(cur_stream)
                 else:
                     d, c = frames[i]
                 poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))      # pose read back = D2H of H,g,e per GN term
@@ -280,7 +294,9 @@ def run_ours(args):
                    "wall_s": round(res["wall"], 3)},
         "clocks": res["clocks"],
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": int(640 * (res_e2e["sdf_evals"] + res_e2e["rgb_evals"]) / n_frames)},
+                # per frame the host reads: a 16-byte record per evaluation (incl. one look-ahead launch per group), the
+                # 96-byte pose when a group ends (3 groups) and the 4-byte row count of the front end
+                "d2h_bytes_per_step": int(16 * (max(res_e2e["sdf_evals"], res_e2e["rgb_evals"]) / n_frames + 3) + 96 * 3 + 4)},
         "gpu_launches": int(res["launches"]),
         "roofline": {"bound": "tensor", "kernel": "gn_eval_kernel (tcgen05 FP16 engine: one Gauss-Newton evaluation = decoder fwd+bwd+JtJ over "
                                "the frame's points, photometric pixels, 6x6 solve; FLOPs counted: decoder only)",

@@ -31,13 +31,19 @@ struct McArgs {
   int* n_tri;
 };
 
-// mc_interp_kernel.cu:7-29
-__device__ __forceinline__ float2 query_raw(const McArgs& A, int bx, int by, int bz, int ax, int ay, int az) {
-  const float2 nan2 = make_float2(CUDART_NAN_F, CUDART_NAN_F);
-  if (bx < 0 || by < 0 || bz < 0 || bx >= A.nx || by >= A.ny || bz >= A.nz) return nan2;   // uint wrap in the reference
+// mc_interp_kernel.cu:7-17: cube batch of voxel (bx, by, bz), -1 when it is outside the grid, unallocated or not in this
+// extraction.  The CTA resolves its 27 neighbours once (nb[] in shared memory) instead of once per corner per neighbour.
+__device__ __forceinline__ int voxel_batch(const McArgs& A, int bx, int by, int bz) {
+  if (bx < 0 || by < 0 || bz < 0 || bx >= A.nx || by >= A.ny || bz >= A.nz) return -1;   // uint wrap in the reference
   const long long vec = A.indexer[((long long)bx * A.ny + by) * A.nz + bz];
-  if (vec == -1 || vec >= A.n_map) return nan2;
-  const int batch = A.mapping[vec];
+  if (vec == -1 || vec >= A.n_map) return -1;
+  return A.mapping[vec];
+}
+
+// mc_interp_kernel.cu:18-29; (dx, dy, dz) in {-1, 0, 1}: which neighbour of the CTA's voxel
+__device__ __forceinline__ float2 query_raw(const McArgs& A, const int* nb, int dx, int dy, int dz, int ax, int ay, int az) {
+  const float2 nan2 = make_float2(CUDART_NAN_F, CUDART_NAN_F);
+  const int batch = nb[(dx + 1) * 9 + (dy + 1) * 3 + (dz + 1)];
   if (batch == -1) return nan2;
   const int R = 2 * A.r;
   const size_t off = (((size_t)batch * R + ax) * R + ay) * R + az;
@@ -46,7 +52,7 @@ __device__ __forceinline__ float2 query_raw(const McArgs& A, int bx, int by, int
 
 // mc_interp_kernel.cu:34-185 (STD_W_SDF variant): tent-weighted blend over the 2x2x2 nearest voxel centres, each
 // weight multiplied by that voxel's predicted std; NaN if the voxel owning this half is missing.
-__device__ float2 blend(const McArgs& A, int bx, int by, int bz, int rx, int ry, int rz) {
+__device__ float2 blend(const McArgs& A, const int* nb, int rx, int ry, int rz) {
   const int r = A.r;
   const int rbound = (r - 1) / 2, rstart = r / 2;
   const float rmid = r / 2.0f;
@@ -72,7 +78,7 @@ __device__ float2 blend(const McArgs& A, int bx, int by, int bz, int rx, int ry,
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int sx = (c >> 2) & 1, sy = (c >> 1) & 1, sz = c & 1;
-    const float2 v = query_raw(A, bx + (sx ? bp[0] : bm[0]), by + (sy ? bp[1] : bm[1]), bz + (sz ? bp[2] : bm[2]),
+    const float2 v = query_raw(A, nb, sx ? bp[0] : bm[0], sy ? bp[1] : bm[1], sz ? bp[2] : bm[2],
                                qx + (sx ? rp[0] : rm[0]), qy + (sy ? rp[1] : rm[1]), qz + (sz ? rp[2] : rm[2]));
     const float w = (sx ? wp[0] : wm[0]) * (sy ? wp[1] : wm[1]) * (sz ? wp[2] : wm[2]);
     if (!isnan(v.x)) {
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(MC_T) mc_kernel(McArgs A) {
   float2* corner = reinterpret_cast<float2*>(mc_smem_raw);
   __shared__ int s_warp[MC_T / 32];
   __shared__ int s_base;
+  __shared__ int nb[27];
   const int r = A.r, r1 = r + 1;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float sbs = 1.0f / r;
@@ -113,9 +120,11 @@ __global__ void __launch_bounds__(MC_T) mc_kernel(McArgs A) {
     const long long vb = A.valid_blocks[lif];
     const int bx = (int)((vb / ((long long)A.ny * A.nz)) % A.nx), by = (int)((vb / A.nz) % A.ny), bz = (int)(vb % A.nz);
     __syncthreads();
+    if (tid < 27) nb[tid] = voxel_batch(A, bx + tid / 9 - 1, by + (tid / 3) % 3 - 1, bz + tid % 3 - 1);
+    __syncthreads();
     for (int c = tid; c < r1 * r1 * r1; c += MC_T) {
       const int cx = c / (r1 * r1), cy = (c / r1) % r1, cz = c % r1;
-      corner[c] = blend(A, bx, by, bz, cx, cy, cz);
+      corner[c] = blend(A, nb, cx, cy, cz);
     }
     __syncthreads();
     const int r3 = r * r * r;

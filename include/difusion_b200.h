@@ -192,10 +192,10 @@ int dfb_sdf_hg(const dfb_map_params* h_params, const float* obs_xyz, int n, cons
 
 /* SDFTracker.gauss_newton (tracker.py:225-288) as ONE host call: for every group of the iteration config, up to n_iter
  * Gauss-Newton steps plus one evaluation-only pass, each evaluating the fused SDF term and/or the fused photometric
- * term.  The loop state lives on the device: a single-thread step kernel after the term kernels scales and adds the
+ * term.  The loop state lives on the device: a one-warp step (the tail of the evaluation's last block) scales and adds the
  * terms, solves the 6x6 system and updates the pose in float64, rolls a step back when its energy rises (which ends the
  * group, tracker.py:269-271) and publishes the pose of the next evaluation, so nothing is read back between
- * iterations; the host keeps one evaluation of look-ahead queued and only polls a 128-byte record per step.
+ * iterations; the host keeps one evaluation of look-ahead queued and only polls a 16-byte record per step (the 96-byte pose follows when a group ends).
  * obs_xyz holds n rows; if d_n (device int32, may be NULL) is given, only the first min(n, max(*d_n, 0)) rows are used, so
  * the caller need not read the row count of dfb_preprocess_frame back before queueing the solve.
  * Poses are 12 doubles: R row-major (9) then t (3).  h_delta_pose is in/out (initial guess -> result; untouched on error).

@@ -162,7 +162,7 @@ void launch_hg_expand(const double* packed, double* out44, cudaStream_t s);
 
 // ---- device-resident Gauss-Newton state (gauss_newton.cu) ------------------------------------------------------------
 // The term kernels of a Gauss-Newton evaluation read their pose from here and add their packed sums here; the
-// single-thread step kernel that follows them consumes the sums, solves, updates the pose and publishes the pose blocks
+// one-warp step that follows them (gn_step.cuh) consumes the sums, solves, updates the pose and publishes the pose blocks
 // of the next evaluation, so the host never has to read H, g back between iterations.
 struct GnShared {
   double sums[2][32];        // packed 29 sums of the SDF term [0] and the photometric term [1]; zero between evaluations

@@ -1,12 +1,14 @@
 // Native Gauss-Newton driver: system/tracker.py:225-288 (gauss_newton) with the two fused terms, device-resident.
-// One C call runs the whole pose solve of a frame.  An evaluation ("slot") is up to three launches on the caller's stream:
+// One C call runs the whole pose solve of a frame.  An evaluation ("slot") is ONE launch on the caller's stream with the
+// tcgen05 engine (decoder_tc.cu gn_eval_kernel: SDF tiles + photometric pixels + the step as the tail of the last
+// block), one launch for photometric-only groups (photometric.cu rgb_step_gn_kernel), and
 //   [SDF term kernel] [photometric term kernel] [gn_step_kernel <<<1, 32>>>]
-// The term kernels read their pose from GnShared and add their packed sums there; the step kernel scales and sums the
-// terms, applies the accept / rollback rule, solves the 6x6 system (float64 LU, partial pivoting), composes the SE(3)
-// update, publishes the pose blocks of the next evaluation and writes a small record into pinned host memory.  The host
-// keeps ONE slot of look-ahead: slot k+1 is enqueued before the record of slot k is read, so the GPU never waits for
-// the host between evaluations; when slot k ends its group (energy rose -> rollback, tracker.py:269-271) the launches
-// of slot k+1 see done[group] and return immediately.
+// with the FP32 engine.  The term code reads its pose from GnShared and adds its packed sums there; the step
+// (gn_step.cuh) scales and sums the terms, applies the accept / rollback rule, solves the 6x6 system (float64 LU,
+// partial pivoting), composes the SE(3) update, publishes the pose blocks of the next evaluation and writes a small
+// record into pinned host memory.  The host keeps ONE slot of look-ahead: slot k+1 is enqueued before the record of
+// slot k is read, so the GPU never waits for the host between evaluations; when slot k ends its group (energy rose ->
+// rollback, tracker.py:269-271) the launch of slot k+1 sees done[group] and returns immediately.
 // Pose algebra restated from utils/motion_util.py:205-228 (from_twist), :275-279 (inv, dot).
 #include <math.h>
 #include <string.h>

@@ -121,3 +121,26 @@ def test_native_gauss_newton_equals_python_loop(weights, T):
     for (Ra, ta), (Rb, tb) in zip(poses[True][0], poses[False][0]):
         # both drivers cast the f64 poses to fp32 for the kernels; 1-ulp differences there are the only divergence
         assert np.abs(Ra - Rb).max() < 1e-6 and np.abs(ta - tb).max() < 1e-6
+
+
+def test_graph_front_end_equals_eager(weights, T):
+    """The CUDA-graph front end (captured on the 2nd / 3rd call, replayed afterwards, two graphs alternating) returns
+    exactly what the eager launches return, frame after frame; depth_cut inside the graph == clipping before the call."""
+    d = pkg()
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    m = make_map(weights)
+    trk_g, trk_e = d.SDFTracker(m, ns(TRACKING)), d.SDFTracker(m, ns(TRACKING))
+    trk_e.graph_frontend = False
+    for rep in range(6):
+        rgb, depth = _frame(T, rep % 3)
+        raw = depth.clone()
+        raw[torch.isnan(raw)] = 7.0                                  # out-of-range instead of NaN: the cut has work to do
+        out_g = trk_g._frontend_graphed(rgb, raw, calib, (0.5, 5.0))
+        out_e = trk_e._frontend(rgb, depth, calib, None)
+        torch.cuda.synchronize()
+        n_g, n_e = int(out_g[5].item()), int(out_e[5].item())
+        assert n_g == n_e and n_g > 1000
+        for a, b in zip(out_g[0] + out_g[1] + out_g[2], out_e[0] + out_e[1] + out_e[2]):      # pyramids, gradients
+            assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+        assert torch.equal(out_g[3][:n_g], out_e[3][:n_e]) and torch.equal(out_g[4][:n_g], out_e[4][:n_e])
+    assert len(trk_g._fe_graphs) == 2

@@ -89,13 +89,23 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, 
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
   }
+  // warp results meet in shared memory: six global atomics per block instead of six per warp (the atomics all hit the
+  // same six words, so their number is the kernel's latency)
+  __shared__ float s_mn[8][3], s_mx[8][3];
+  const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (mn[a] <= mx[a]) {
-        atomicMin(&bbox[a], f2ord(mn[a]));
-        atomicMax(&bbox[3 + a], f2ord(mx[a]));
-      }
+    for (int a = 0; a < 3; ++a) { s_mn[w][a] = mn[a]; s_mx[w][a] = mx[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    float lo = s_mn[0][a], hi = s_mx[0][a];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) { lo = fminf(lo, s_mn[ww][a]); hi = fmaxf(hi, s_mx[ww][a]); }
+    if (lo <= hi) {
+      atomicMin(&bbox[a], f2ord(lo));
+      atomicMax(&bbox[3 + a], f2ord(hi));
     }
   }
 }

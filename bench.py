@@ -145,8 +145,19 @@ def make_system(dfb, device):
 
 
 def gen_frames(dfb, n, device, seed):
+    """Synthetic frames in the form a dataset delivers them: 16-bit depth (1/5000 m) and 8-bit colour, as pinned host
+    buffers (`raw`), plus the float32 tensors the frame-ingest kernel makes of them, resident on the device."""
     seq = dfb.synth.SyntheticSequence(n_frames=n, device=device, seed=seed)
-    return [seq.frame(i) for i in range(n)], seq
+    frames, raw = [], []
+    for i in range(n):
+        depth, rgb = seq.frame(i)
+        d16 = np.round(depth.cpu().numpy() * 5000.0).astype(np.uint16)
+        c8 = np.round(np.clip(rgb.cpu().numpy(), 0.0, 1.0) * 255.0).astype(np.uint8)
+        hd = torch.from_numpy(d16.view(np.int16)).view(torch.uint16).pin_memory()
+        hc = torch.from_numpy(c8).pin_memory()
+        raw.append((hd, hc))
+        frames.append(dfb.ext.ingest_frame(hd.to(device), hc.to(device), 5000.0))
+    return frames, raw, seq
 
 
 def refresh(dfb, m, trk, frame_id, depth, rgb, calib, first_iso, integrate_interval=20, depth_cut=(0.5, 5.0)):
@@ -173,9 +184,8 @@ def run_ours(args):
     n_frames = K + Wm
     calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
     first_iso = dfb.Isometry(q=dfb.Quaternion(array=dfb.synth.FIRST_TQ[3:]), t=np.array(dfb.synth.FIRST_TQ[:3]))
-    frames, seq = gen_frames(dfb, n_frames, dev, seed=rank)          # synthetic input, generated on the device, untimed
-    host_frames = [(d.cpu().pin_memory(), c.cpu().pin_memory()) for d, c in frames]
-    h2d = frames[0][0].numel() * 4 + frames[0][1].numel() * 4
+    frames, host_frames, seq = gen_frames(dfb, n_frames, dev, seed=rank)   # synthetic input, generated on the device, untimed
+    h2d = host_frames[0][0].numel() * 2 + host_frames[0][1].numel()         # raw uint16 depth + uint8 colour: 5 bytes per pixel
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -200,17 +210,20 @@ def run_ours(args):
         copy_stream = torch.cuda.Stream(dev)
 
         def upload(i):
-            """H2D of frame i's depth + colour from pinned memory on the copy stream (double-buffered: issued while the
+            """H2D of frame i's raw depth + colour from pinned memory on the copy stream (double-buffered: issued while the
             previous frame is being processed, like frames arriving from a camera)."""
             with torch.cuda.stream(copy_stream):
                 d_ = host_frames[i][0].to(dev, non_blocking=True); c_ = host_frames[i][1].to(dev, non_blocking=True)
                 ev_ = torch.cuda.Event(); ev_.record(copy_stream)
             return d_, c_, ev_
+
+        def ingest(d_raw, c_raw):
+            return dfb.ext.ingest_frame(d_raw, c_raw, 5000.0)       # uint16 / uint8 -> float32 (icl_nuim.py:110-114)
         trk.time_kernels = time_kernels
         sampler = ClockSampler(local)                        # NVML is opened here, outside the timed region
         for i in range(Wm):
             l2_flush.zero_()
-            d, c = (t.to(dev, non_blocking=True) for t in host_frames[i]) if e2e else frames[i]
+            d, c = ingest(*(t.to(dev, non_blocking=True) for t in host_frames[i])) if e2e else frames[i]
             poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))
         trk.compute_sdf_Hg = timed_sdf
         trk.sdf_kernel_us = 0; trk.sdf_queries_J = 0; trk.sdf_queries_noJ = 0
@@ -232,6 +245,7 @@ def run_ours(args):
                     cur_stream = torch.cuda.current_stream()
                     cur_stream.wait_event(ev_up)
                     d.record_stream(cur_stream); c.record_stream(cur_stream)
+                    d, c = ingest(d, c)
                 else:
                     d, c = frames[i]
                 poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))      # pose read back = D2H of H,g,e per GN term

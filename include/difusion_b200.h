@@ -65,6 +65,15 @@ int dfb_get_encoder_engine(void);
  * ---------------------------------------------------------------------------------------------- */
 /* system.ext.unproject_depth (imgproc.cpp:3, imgproc.cu:5-44).  depth (H,W) f32, NaN = invalid ->
  * pc (H,W,3) f32.  Invalid pixels get NaN in ALL three channels (the reference leaves 1,2 uninitialised). */
+/* Frame ingest: replaces dataset/production/icl_nuim.py:110-114 (cv2 decode -> float32 -> .cuda() -> / 5000, / 255.) and the
+ * clipping of main.py:56-57.  depth_raw uint16[H,W] and color_raw uint8[H,W,3] are DEVICE copies of the decoded PNGs;
+ * depth_out[i] = depth_raw[i] / depth_scale (NaN outside [cut_min, cut_max] when cut_min < cut_max),
+ * rgb_out = color_raw / 255 with an optional BGR -> RGB swap.  div_mode: DFB_DIV_RECIP multiplies by the fp32 reciprocal
+ * like torch CUDA's tensor / scalar (what the reference executes), DFB_DIV_IEEE divides (numpy / torch CPU).
+ * Either pair (depth_raw, depth_out) or (color_raw, rgb_out) may be NULL. */
+int dfb_ingest_frame(const uint16_t* depth_raw, const uint8_t* color_raw, int H, int W, float depth_scale, int div_mode,
+                     float cut_min, float cut_max, int bgr, float* depth_out, float* rgb_out, void* stream);
+
 int dfb_unproject_depth(const float* depth, int H, int W, float fx, float fy, float cx, float cy, float* pc,
                         void* stream);
 

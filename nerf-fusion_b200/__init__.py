@@ -7,11 +7,11 @@ The directory name has a hyphen; import it as ``nerf_fusion_b200`` (alias module
 ``importlib.import_module("nerf-fusion_b200")``.
 """
 from . import _lib, weights, motion, synth          # noqa: F401  (no torch.cuda needed)
-from . import ext, map, tracker, sharded            # noqa: F401
+from . import ext, map, tracker, sharded, dataset   # noqa: F401
 from .map import DenseIndexedMap                    # noqa: F401
 from .tracker import SDFTracker, FrameIntrinsic     # noqa: F401
 from .motion import Isometry, Quaternion            # noqa: F401
 from ._lib import DfbError                          # noqa: F401
 
-__all__ = ["ext", "map", "tracker", "motion", "weights", "synth", "sharded", "DenseIndexedMap", "SDFTracker", "FrameIntrinsic",
+__all__ = ["ext", "map", "tracker", "motion", "weights", "synth", "sharded", "dataset", "DenseIndexedMap", "SDFTracker", "FrameIntrinsic",
            "Isometry", "Quaternion", "DfbError"]

@@ -32,6 +32,28 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
   pc[3 * i + 2] = z;
 }
 
+// Frame ingest (dataset/production/icl_nuim.py:110-114 + main.py:56-57): the raw 16-bit depth PNG and 8-bit colour image are
+// uploaded as they are (5 bytes/pixel instead of 16) and converted here: depth = raw / scale, colour = raw / 255, optional
+// BGR -> RGB swap (cv2.cvtColor in the reference), optional clipping to NaN outside [cut_min, cut_max].
+__global__ void __launch_bounds__(256) ingest_kernel(const uint16_t* __restrict__ depth_raw, const uint8_t* __restrict__ color_raw, int n,
+                                                     float scale, float inv_scale, int div_mode, float cut_min, float cut_max, int bgr,
+                                                     float* __restrict__ depth_out, float* __restrict__ rgb_out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  if (depth_raw) {
+    float d = div_vs((float)depth_raw[i], scale, inv_scale, div_mode);
+    if (cut_min < cut_max && (d < cut_min || d > cut_max)) d = CUDART_NAN_F;
+    depth_out[i] = d;
+  }
+  if (color_raw) {
+    const float c0 = (float)color_raw[3 * i], c1 = (float)color_raw[3 * i + 1], c2 = (float)color_raw[3 * i + 2];
+    const float inv255 = 1.0f / 255.0f;
+    rgb_out[3 * i + 0] = div_vs(bgr ? c2 : c0, 255.0f, inv255, div_mode);
+    rgb_out[3 * i + 1] = div_vs(c1, 255.0f, inv255, div_mode);
+    rgb_out[3 * i + 2] = div_vs(bgr ? c0 : c2, 255.0f, inv255, div_mode);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // uniform grid
 // ------------------------------------------------------------------------------------------------
@@ -602,6 +624,17 @@ int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radi
   int rc = build_grid(pc4, n, radius, GRID_CAP_COARSE, w, s);
   if (rc) return rc;
   radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask, nullptr);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_ingest_frame(const uint16_t* depth_raw, const uint8_t* color_raw, int H, int W, float depth_scale, int div_mode, float cut_min,
+                     float cut_max, int bgr, float* depth_out, float* rgb_out, void* stream) {
+  DFB_CHECK_ARG(H >= 0 && W >= 0 && depth_scale > 0.f, "ingest_frame");
+  if (H * W == 0) return DFB_OK;
+  DFB_CHECK_ARG((depth_raw == nullptr) == (depth_out == nullptr) && (color_raw == nullptr) == (rgb_out == nullptr), "ingest_frame: in/out pairs");
+  ingest_kernel<<<div_up((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(depth_raw, color_raw, H * W, depth_scale, 1.0f / depth_scale,
+                                                                                div_mode, cut_min, cut_max, bgr, depth_out, rgb_out);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -53,6 +53,34 @@ class Workspace:
 _WS = Workspace()
 
 
+# ----------------------------------------------------------------------------------------------- frame ingest
+def ingest_frame(depth_raw=None, color_raw=None, depth_scale=5000.0, depth_cut=None, bgr=False, div_mode=1):
+    """dataset/production/icl_nuim.py:110-114 (+ main.py:56-57 when depth_cut is given) on the device: depth_raw uint16[H,W]
+    and / or color_raw uint8[H,W,3] (CUDA copies of the decoded images) -> (depth f32[H,W] | None, rgb f32[H,W,3] | None).
+    div_mode 1 = multiply by the fp32 reciprocal (torch CUDA's tensor / scalar, what the reference runs), 0 = IEEE divide."""
+    ref = depth_raw if depth_raw is not None else color_raw
+    if ref is None:
+        raise ValueError("ingest_frame needs depth_raw and / or color_raw")
+    if depth_raw is not None:
+        if depth_raw.dtype not in (torch.uint16, torch.int16):
+            raise RuntimeError("depth_raw must be a 16-bit integer tensor (the PNG's uint16 payload)")
+        _chk(depth_raw, "depth_raw", depth_raw.dtype)
+    if color_raw is not None:
+        _chk(color_raw, "color_raw", torch.uint8)
+        if color_raw.dim() != 3 or color_raw.size(2) != 3:
+            raise RuntimeError("color_raw must be (H, W, 3)")
+    H, W = int(ref.shape[0]), int(ref.shape[1])
+    depth = torch.empty((H, W), dtype=torch.float32, device=ref.device) if depth_raw is not None else None
+    rgb = torch.empty((H, W, 3), dtype=torch.float32, device=ref.device) if color_raw is not None else None
+    lo, hi = (float(depth_cut[0]), float(depth_cut[1])) if depth_cut is not None else (0.0, 0.0)
+    with torch.cuda.device(ref.device):
+        check(_lib.load().dfb_ingest_frame(_p(depth_raw) if depth_raw is not None else None,
+                                           _p(color_raw) if color_raw is not None else None, H, W, float(depth_scale), int(div_mode),
+                                           lo, hi, int(bool(bgr)), _p(depth) if depth is not None else None,
+                                           _p(rgb) if rgb is not None else None, _stream()))
+    return depth, rgb
+
+
 # ----------------------------------------------------------------------------------------------- imgproc
 def unproject_depth(depth, fx, fy, cx, cy):
     """system.ext.unproject_depth (imgproc.cpp:3): depth f32[H,W] -> f32[H,W,3]."""

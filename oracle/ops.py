@@ -16,6 +16,26 @@ def _fma(a, b, c):
 # ----------------------------------------------------------------------------------------------
 # imgproc
 # ----------------------------------------------------------------------------------------------
+def ingest_frame(depth_raw, color_raw, depth_scale=5000.0, depth_cut=None, bgr=False, recip=True):
+    """dataset/production/icl_nuim.py:110-114: depth = float32(raw) / calib[4] and rgb = float32(raw) / 255. -- both executed
+    by torch on CUDA tensors in the reference, i.e. as a multiply by the fp32 reciprocal (recip=True); numpy's true divide
+    with recip=False.  main.py:56-57: depths outside [cut_min, cut_max] -> NaN.  bgr: cv2.cvtColor(BGR2RGB), :112."""
+    out_d = out_c = None
+    if depth_raw is not None:
+        d = np.asarray(depth_raw).astype(f32)
+        out_d = (d * (f32(1.0) / f32(depth_scale))).astype(f32) if recip else (d / f32(depth_scale)).astype(f32)
+        if depth_cut is not None:
+            out_d = out_d.copy()
+            out_d[(out_d < f32(depth_cut[0])) | (out_d > f32(depth_cut[1]))] = np.nan
+    if color_raw is not None:
+        c = np.asarray(color_raw).astype(f32)
+        if bgr:
+            c = c[..., ::-1]
+        out_c = (c * (f32(1.0) / f32(255.0))).astype(f32) if recip else (c / f32(255.0)).astype(f32)
+        out_c = np.ascontiguousarray(out_c)
+    return out_d, out_c
+
+
 def unproject_depth(depth, fx, fy, cx, cy):
     """imgproc.cu:5-23.  depth (H,W) f32, NaN = invalid.  Returns (H,W,3) f32.
     The reference writes only channel 0 (=NaN) for invalid pixels and leaves channels 1,2

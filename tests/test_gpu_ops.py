@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import nets, ops
-from util import pkg
+from util import GOLD, pkg
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -183,3 +183,32 @@ def test_encoder_and_decoder_forward(weights):
     np.testing.assert_allclose(std.cpu().numpy(), rd.numpy(), atol=2e-6)
     s0, _ = d.ext.decoder_forward(torch.zeros((0, 32), device=DEV), dblob)
     assert s0.numel() == 0
+
+
+def test_ingest_frame_and_reader(tmp_path):
+    """dfb_ingest_frame against the reference reader's outputs (IEEE mode = torch CPU, bit-exact), the reciprocal mode against
+    the oracle (what torch CUDA computes for tensor / scalar), and the whole ICLNUIMSequence reader on a PNG sequence."""
+    from test_dataset_cpu import _write_sequence
+    from oracle import ops as O
+    d = pkg()
+    D = dict(np.load(GOLD / "dataset_golden.npz"))
+    for i in range(int(D["n_frames"])):
+        d16 = torch.from_numpy(D[f"f{i}_depth_u16"].view(np.int16)).view(torch.uint16).to(DEV)
+        c8 = torch.from_numpy(D[f"f{i}_bgr_u8"]).to(DEV)
+        dep, rgb = d.ext.ingest_frame(d16, c8, 5000.0, None, bgr=True, div_mode=0)
+        assert np.array_equal(dep.cpu().numpy(), D[f"f{i}_depth"]) and np.array_equal(rgb.cpu().numpy(), D[f"f{i}_rgb"])
+        dep1, rgb1 = d.ext.ingest_frame(d16, c8, 5000.0, (0.5, 5.0), bgr=True, div_mode=1)
+        od, oc = O.ingest_frame(D[f"f{i}_depth_u16"], D[f"f{i}_bgr_u8"], 5000.0, (0.5, 5.0), bgr=True, recip=True)
+        assert np.array_equal(np.nan_to_num(dep1.cpu().numpy(), nan=-1.0), np.nan_to_num(od, nan=-1.0))
+        assert np.array_equal(rgb1.cpu().numpy(), oc)
+        only_d, none = d.ext.ingest_frame(d16, None)
+        assert none is None and only_d.shape == d16.shape
+    pytest.importorskip("cv2")
+    _write_sequence(D, tmp_path)
+    seq = d.dataset.ICLNUIMSequence(str(tmp_path), 0, -1, D["first_tq"].tolist(), load_gt=True, device=DEV)
+    assert len(seq) == int(D["n_frames"])
+    for i, fd in enumerate(seq):
+        od, oc = O.ingest_frame(D[f"f{i}_depth_u16"], D[f"f{i}_bgr_u8"], 5000.0, None, bgr=True, recip=True)
+        assert np.array_equal(fd.depth.cpu().numpy(), od) and np.array_equal(fd.rgb.cpu().numpy(), oc)
+        assert np.abs(fd.depth.cpu().numpy() - D[f"f{i}_depth"]).max() < 1e-6          # reciprocal vs IEEE: 1 ulp
+        assert np.abs(fd.gt_pose.t - D[f"f{i}_gt_t"]).max() < 1e-12 and fd.calib.dscale == 5000.0

@@ -5,7 +5,7 @@ import numpy as np, torch
 import bench
 dfb = importlib.import_module("nerf-fusion_b200")
 dev = "cuda:0"
-frames, seq = bench.gen_frames(dfb, 45, dev, 0)
+frames, _raw, seq = bench.gen_frames(dfb, 45, dev, 0)
 m, trk = bench.make_system(dfb, dev)
 calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
 first = dfb.Isometry(q=dfb.Quaternion(array=dfb.synth.FIRST_TQ[3:]), t=np.array(dfb.synth.FIRST_TQ[:3]))

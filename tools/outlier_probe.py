@@ -8,7 +8,7 @@ dfb = importlib.import_module("nerf-fusion_b200")
 dev = "cuda:0"
 calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
 first_iso = dfb.Isometry(q=dfb.Quaternion(array=dfb.synth.FIRST_TQ[3:]), t=np.array(dfb.synth.FIRST_TQ[:3]))
-frames, seq = bench.gen_frames(dfb, 25, dev, seed=0)
+frames, _raw, seq = bench.gen_frames(dfb, 25, dev, seed=0)
 l2 = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
 T = {}
 def wrap(obj, name):

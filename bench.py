@@ -180,7 +180,7 @@ def run_ours(args):
         torch.set_num_threads(max(1, min(8, (os.cpu_count() or 1) // world)))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
-    K, Wm = args.steps, args.warmup
+    K, Wm = args.steps, max(args.warmup, 3)     # >= 3 warm-up frames: eager frame, then the two front-end graphs are captured
     n_frames = K + Wm
     calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
     first_iso = dfb.Isometry(q=dfb.Quaternion(array=dfb.synth.FIRST_TQ[3:]), t=np.array(dfb.synth.FIRST_TQ[:3]))

@@ -144,3 +144,32 @@ def test_graph_front_end_equals_eager(weights, T):
             assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
         assert torch.equal(out_g[3][:n_g], out_e[3][:n_e]) and torch.equal(out_g[4][:n_g], out_e[4][:n_e])
     assert len(trk_g._fe_graphs) == 2
+
+
+def test_pose_parity_on_the_reference_points(weights, T):
+    """North-star pose tolerance (1e-5) where it is well-posed: the solve is fed the reference's OWN preprocessed points
+    (golden f_i_pc), map built from its keyframe cloud, previous pose = its previous pose.  What differs is only what this
+    path computes: image pyramid, photometric term, SDF term (FP32 engine), device-resident Gauss-Newton.  Measured: 3e-7."""
+    d = pkg()
+    m = make_map(weights)
+    cfg = dict(TRACKING)
+    cfg["iter_config"] = [{"n": int(T["iter_config_n"][0]), "type": [["rgb", 2]]},
+                          {"n": int(T["iter_config_n"][1]), "type": [["sdf"], ["rgb", 1]]},
+                          {"n": int(T["iter_config_n"][2]), "type": [["sdf"], ["rgb", 0]]}]
+    trk = d.SDFTracker(m, ns(cfg))
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    pose0 = d.Isometry.from_matrix(T["f0_pose_R"], T["f0_pose_t"])
+    pc0, n0 = torch.from_numpy(T["f0_pc"]).to(DEV), torch.from_numpy(T["f0_normal"]).to(DEV)
+    m.integrate_keyframe(pose0 @ pc0, pose0.rotation @ n0)
+    assert m.n_occupied == int(T["n_occupied_after_f0"])
+    for i in (1, 2):
+        (rgb_p, dep_p), (rgb_c, dep_c) = _frame(T, i - 1), _frame(T, i)
+        Ip, Dp, _ = trk._make_image_pyramid(rgb_p.mean(-1), dep_p)
+        Ic, Dc, Gc = trk._make_image_pyramid(rgb_c.mean(-1), dep_c)
+        trk.last_intensity, trk.last_depth = Ip, Dp
+        last = d.Isometry.from_matrix(T[f"f{i - 1}_pose_R"], T[f"f{i - 1}_pose_t"])
+        trk.all_pd_pose = [last]
+        pose = trk.gauss_newton(last.dot(d.Isometry()), Ic, Dc, Gc, torch.from_numpy(T[f"f{i}_pc"]).to(DEV), calib)
+        dt = np.abs(pose.t - T[f"f{i}_pose_t"]).max(); dR = np.abs(pose.q.rotation_matrix - T[f"f{i}_pose_R"]).max()
+        print("frame", i, "pose vs reference golden: t %.2e R %.2e" % (dt, dR))
+        assert dt < 1e-5 and dR < 1e-5

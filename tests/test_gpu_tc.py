@@ -217,3 +217,33 @@ def test_gn_error_paths_tc(weights, engines):
     good = torch.from_numpy(G["Pc"]).to(DEV)
     pose = trk.gauss_newton(last.dot(d.Isometry()), None, None, None, good, None)
     assert np.isfinite(pose.t).all()
+
+
+def test_tc_engine_tracks_like_fp32_engine_full_resolution(weights, engines):
+    """640x480 synthetic sequence (the bench workload): the tcgen05 engines' poses against the FP32 engines' poses and against
+    the synthetic ground truth.  Measured: median difference 2e-5 m, worst frame 3e-4 m; both ~1 mm from the ground truth."""
+    from util import TRACKING, ns
+    d = pkg()
+    seq = d.synth.SyntheticSequence(n_frames=8, device=DEV, seed=0)
+    frames = [seq.frame(i) for i in range(8)]
+    calib = d.FrameIntrinsic(*d.synth.ICL_CALIB)
+    first = d.Isometry(q=d.Quaternion(array=d.synth.FIRST_TQ[3:]), t=np.array(d.synth.FIRST_TQ[:3]))
+    res = {}
+    for eng in (0, 1):
+        engines.dfb_set_decoder_engine(eng); engines.dfb_set_encoder_engine(eng)
+        m = make_map(weights)
+        trk = d.SDFTracker(m, ns(TRACKING))
+        out = []
+        for i, (depth, rgb) in enumerate(frames):
+            pose = trk.track_camera(rgb, depth, calib, first if i == 0 else None, depth_cut=(0.5, 5.0))
+            if i == 0:
+                pc, nrm = trk.last_processed_pc
+                m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+            out.append(pose.t.copy())
+        res[eng] = np.array(out)
+    diff = np.abs(res[0] - res[1]).max(1)
+    gt = np.array([seq.poses[i][1] for i in range(8)])
+    print("engine difference per frame:", np.array2string(diff, precision=1), "| error vs ground truth fp32 %.2e tcgen05 %.2e" % (
+        np.abs(res[0] - gt).max(), np.abs(res[1] - gt).max()))
+    assert np.median(diff) < 1e-4 and diff.max() < 1e-3
+    assert np.abs(res[0] - gt).max() < 5e-3 and np.abs(res[1] - gt).max() < 5e-3

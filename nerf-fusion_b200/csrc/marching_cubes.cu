@@ -152,9 +152,21 @@ __global__ void __launch_bounds__(MC_T) mc_kernel(McArgs A) {
       // pass 1: count surviving triangles of this cell; pass 2: write them
       uint64_t row = kMcTriTable[cube_type];
       int my_off = 0;
+      // A vertex std is a convex combination of two corner stds: when no corner exceeds max_std (always, with the
+      // reference's default 2000) no triangle can be dropped and the counting pass only walks the table.
+      bool may_drop = false;
+      if (cube_type != 0) {
+        float smax = sd[0];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) smax = fmaxf(smax, sd[c]);
+        may_drop = !(smax <= A.max_std);
+      }
       for (int pass = 0; pass < 2; ++pass) {
         int k = 0;
         uint64_t rr = row;
+        if (pass == 0 && !may_drop) {
+          while ((rr & 0xF) != 0xF) { ++k; rr >>= 12; }
+        }
         while ((rr & 0xF) != 0xF) {
           float4 vp[3];
 #pragma unroll

@@ -91,10 +91,12 @@ __device__ float2 blend(const McArgs& A, const int* nb, int rx, int ry, int rz) 
   return make_float2(tot_sdf / tot_wsdf, tot_std / tot_w);
 }
 
-__device__ __constant__ int8_t kEdgeA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
-__device__ __constant__ int8_t kEdgeB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
-// corner c -> (dx, dy, dz) packed as bits 0,1,2  (mc_interp_kernel.cu:236-266)
-__device__ __constant__ int8_t kCornerOff[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+// Edge e joins corners edge_a(e) and edge_b(e); corner c sits at offset (dx, dy, dz) = bits 0, 1, 2 of corner_off(c)
+// (mc_interp_kernel.cu:236-266).  The tables {0,1,2,3,4,5,6,7,0,1,2,3}, {1,2,3,0,5,6,7,4,4,5,6,7} and {0,1,3,2,4,5,7,6} are
+// evaluated arithmetically: lanes of a warp look up different entries, which a __constant__ table would serialise.
+__device__ __forceinline__ int edge_a(int e) { return e < 8 ? e : e - 8; }
+__device__ __forceinline__ int edge_b(int e) { return e < 8 ? (e & 4) | ((e + 1) & 3) : e - 4; }
+__device__ __forceinline__ int corner_off(int c) { return c ^ ((c >> 1) & 1); }
 
 // mc_interp_kernel.cu:187-200
 __device__ __forceinline__ float4 sdf_interp(float3 p1, float3 p2, float s1, float s2, float v1, float v2) {
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(MC_T) mc_kernel(McArgs A) {
         bool alive = true;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const int o = kCornerOff[c];
+          const int o = corner_off(c);
           const float2 v = corner[((rx + (o & 1)) * r1 + (ry + ((o >> 1) & 1))) * r1 + (rz + ((o >> 2) & 1))];
           sv[c] = v.x; sd[c] = v.y;
           alive = alive && !isnan(v.x);
@@ -172,8 +174,8 @@ __global__ void __launch_bounds__(MC_T) mc_kernel(McArgs A) {
 #pragma unroll
           for (int vi = 0; vi < 3; ++vi) {
             const int e = (int)((rr >> (4 * vi)) & 0xF);
-            const int ca = kEdgeA[e], cb = kEdgeB[e];
-            const int oa = kCornerOff[ca], ob = kCornerOff[cb];
+            const int ca = edge_a(e), cb = edge_b(e);
+            const int oa = corner_off(ca), ob = corner_off(cb);
             const float3 pa = make_float3(bx + (rx + (oa & 1)) * sbs, by + (ry + ((oa >> 1) & 1)) * sbs, bz + (rz + ((oa >> 2) & 1)) * sbs);
             const float3 pb = make_float3(bx + (rx + (ob & 1)) * sbs, by + (ry + ((ob >> 1) & 1)) * sbs, bz + (rz + ((ob >> 2) & 1)) * sbs);
             vp[vi] = sdf_interp(pa, pb, sd[ca], sd[cb], sv[ca], sv[cb]);

@@ -137,6 +137,9 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spin = 0;; ++spin) {
       if (rec->seq == sl.seq && rec->check == (sl.seq ^ dfb::GN_CHECK)) { __atomic_thread_fence(__ATOMIC_ACQUIRE); break; }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();                     // be polite to the sibling hyper-thread while spinning
+#endif
       if ((spin & 0xfff) == 0xfff) {
         cudaError_t e = cudaStreamQuery(s);
         if (e != cudaSuccess && e != cudaErrorNotReady) { dfb::set_error("gauss_newton: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }

@@ -216,9 +216,17 @@ static __device__ __noinline__ void step_warp(GnShared* gs, const StepArgs a, vo
   const int lane = threadIdx.x & 31;
   STEP_MARK(0);
   {
+    // L2 loads (the sums were produced by atomics of other blocks), all in flight before the first shared-memory store:
+    // interleaved with the stores the compiler must keep them in order (possible aliasing) and pays one L2 latency each
     const double* src = reinterpret_cast<const double*>(gs);
     double* dst = reinterpret_cast<double*>(&sh);
-    for (int i = lane; i < ND; i += 32) dst[i] = __ldcg(src + i);      // L2: the sums were produced by atomics of other blocks
+    constexpr int PER_LANE = (ND + 31) / 32;
+    double v[PER_LANE];
+#pragma unroll
+    for (int k = 0; k < PER_LANE; ++k) v[k] = (lane + 32 * k < ND) ? __ldcg(src + lane + 32 * k) : 0.0;
+#pragma unroll
+    for (int k = 0; k < PER_LANE; ++k)
+      if (lane + 32 * k < ND) dst[lane + 32 * k] = v[k];
   }
   __syncwarp();
   STEP_MARK(1);

@@ -169,6 +169,7 @@ struct GnShared {
   double delta[12], last_delta[12], last[12];   // poses: R row-major (9), t (3)
   double last_energy;
   double intr[4];            // fx, fy, cx, cy
+  double kinv[4];            // 1/fx, 1/fy, -cx/fx, -cy/fy (entries of K^-1)
   float pose_sdf[36];        // PoseDev image of the next SDF evaluation (33 floats used)
   float krk[12], kt[4];      // K R K^-1 (9 used), K t (3 used) of the next photometric evaluation
   int done[8];               // group i finished (converged, rolled back or failed): its remaining launches return at once

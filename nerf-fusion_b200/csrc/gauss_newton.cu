@@ -30,6 +30,7 @@ __global__ void gn_init_kernel(dfb::GnShared* gs, GnInit in) {
   if (t < 64) reinterpret_cast<double*>(gs->sums)[t] = 0.0;
   if (t < 12) { gs->last[t] = in.last[t]; gs->delta[t] = in.delta[t]; gs->last_delta[t] = in.delta[t]; }
   if (t < 4) gs->intr[t] = in.intr[t];
+  if (t == 0) { gs->kinv[0] = 1 / in.intr[0]; gs->kinv[1] = 1 / in.intr[1]; gs->kinv[2] = -in.intr[2] / in.intr[0]; gs->kinv[3] = -in.intr[3] / in.intr[1]; }
   if (t < 8) gs->done[t] = 0;
   if (t == 0) { gs->error = 0; gs->last_energy = CUDART_INF; gs->ticket = 0; gs->rgb_cursor = 0; gs->pad_ = 0; }
   __syncthreads();

@@ -16,7 +16,7 @@ constexpr int STEP_SCRATCH_BYTES = 2048;   // shared-memory scratch the step nee
 
 #ifdef DFB_TC_PROFILE
 static __device__ unsigned long long g_step_prof[16];
-#define STEP_MARK(i) do { if ((threadIdx.x & 31) == 0) g_step_prof[i] = clock64(); } while (0)
+#define STEP_MARK(i) do { if ((threadIdx.x & 31) == 0) g_step_prof[(a.step & 1) * 8 + (i)] = clock64(); } while (0)   /* even / odd steps kept apart */
 #else
 #define STEP_MARK(i) do {} while (0)
 #endif
@@ -99,7 +99,8 @@ __device__ __forceinline__ Pose from_twist(const double* xi) {   // motion_util.
         J[3 * i + j] = (s * ia) * I + (1 - s * ia) * oo + ((1 - c) * ia) * Wa[3 * i + j];
       }
   }
-  renormalise(p.R);
+  // (pyquaternion would normalise the quaternion of this matrix here; Rodrigues' formula already gives a rotation to
+  // rounding, and the composed pose is renormalised by the caller)
   mat3_vec(J, rho, p.t);
   return p;
 }
@@ -112,7 +113,7 @@ __device__ __forceinline__ bool solve6_warp(const double* H, const double* g, do
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int j = lane < 7 ? lane : 6;
-  double a[6];
+  double a[6], ipiv[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) a[r] = (j < 6) ? H[6 * r + j] : -g[r];
   bool ok = true;
@@ -135,10 +136,13 @@ __device__ __forceinline__ bool solve6_warp(const double* H, const double* g, do
       a[c] = sw ? ar : ac;
       a[r] = sw ? ac : ar;
     }
-    const double pc = __shfl_sync(FULL, a[c], c);
+    // one reciprocal per pivot, then multiplies (what LAPACK's dgetf2 does: DSCAL by 1 / A(j,j)); a float64 division costs
+    // several hundred cycles here and the step sits between two evaluations
+    const double ipc = 1.0 / __shfl_sync(FULL, a[c], c);
+    ipiv[c] = ipc;
 #pragma unroll
     for (int r = c + 1; r < 6; ++r) {
-      const double f = __shfl_sync(FULL, a[r], c) / pc;
+      const double f = __shfl_sync(FULL, a[r], c) * ipc;
       a[r] -= f * a[c];
     }
   }
@@ -147,7 +151,7 @@ __device__ __forceinline__ bool solve6_warp(const double* H, const double* g, do
     double sacc = __shfl_sync(FULL, a[r], 6);
 #pragma unroll
     for (int jj = r + 1; jj < 6; ++jj) sacc -= __shfl_sync(FULL, a[r], jj) * x[jj];
-    x[r] = sacc / __shfl_sync(FULL, a[r], r);
+    x[r] = sacc * ipiv[r];
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -170,7 +174,7 @@ __device__ __forceinline__ void publish_pose(GnShared* gs) {
   for (int i = 0; i < 3; ++i) { hp[9 + i] = (float)total.t[i]; hp[21 + i] = (float)delta.t[i]; }
   const double fx = gs->intr[0], fy = gs->intr[1], cx = gs->intr[2], cy = gs->intr[3];
   const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-  const double Kinv[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
+  const double Kinv[9] = {gs->kinv[0], 0, gs->kinv[2], 0, gs->kinv[1], gs->kinv[3], 0, 0, 1};   // 1/fx, 1/fy, -cx/fx, -cy/fy (init kernel)
   double KR[9], KRK[9], Kt[3];
   mat3_mul(K, delta.R, KR); mat3_mul(KR, Kinv, KRK); mat3_vec(K, delta.t, Kt);
   #pragma unroll

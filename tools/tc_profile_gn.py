@@ -33,8 +33,13 @@ for i, v in enumerate(t[:len(names)]):
 
 sb = (C.c_ulonglong * 16)()
 raw.dfb_debug_read_step_prof(sb)
-st = np.array(list(sb)[:8], dtype=np.int64)
 lab = ["enter", "state loaded", "H,g scaled", "solved", "pose updated", "pose published", "state stored", "record written"]
-print("step (last block of the last launch):")
-for i in range(1, 8):
-    print(f"   {lab[i]:16s} +{int(st[i] - st[i - 1]):6d} cycles")
+for half, what in ((0, "step 0 (solve + pose update)"), (1, "step 1 (evaluation-only pass, ends the group)")):
+    st = np.array(list(sb)[8 * half:8 * half + 8], dtype=np.int64)
+    print(what + ":")
+    prev = st[0]
+    for i in range(1, 8):
+        if st[i] < prev:            # phase not executed in this step
+            continue
+        print(f"   {lab[i]:16s} +{int(st[i] - prev):6d} cycles"); prev = st[i]
+    print(f"   total            {int(prev - st[0]):7d} cycles")

@@ -194,6 +194,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Warm the caching allocator: on these boxes a cudaMalloc takes 1-70 ms, and a keyframe or an upload that needs a fresh
+    # segment inside the ~70 ms timed region shows up as a 3-8 ms frame.  Cached segments make every later request a reuse.
+    warm = [torch.empty(900 * 1024, dtype=torch.uint8, device=dev) for _ in range(96)] + \
+           [torch.empty(8 << 20, dtype=torch.uint8, device=dev) for _ in range(32)]
+    del warm
+
     def run(e2e, time_kernels=False):
         m, trk = make_system(dfb, dev)
         hg_events = []
@@ -223,19 +229,30 @@ def run_ours(args):
         sampler = ClockSampler(local)                        # NVML is opened here, outside the timed region
         for i in range(Wm):
             l2_flush.zero_()
-            d, c = ingest(*(t.to(dev, non_blocking=True) for t in host_frames[i])) if e2e else frames[i]
+            if e2e:                                          # same path as the timed loop (the copy stream has its own allocator pool)
+                d, c, ev_up = upload(i)
+                torch.cuda.current_stream().wait_event(ev_up)
+                d.record_stream(torch.cuda.current_stream()); c.record_stream(torch.cuda.current_stream())
+                d, c = ingest(d, c)
+            else:
+                d, c = frames[i]
             poses.append(refresh(dfb, m, trk, i, d, c, calib, first_iso))
         trk.compute_sdf_Hg = timed_sdf
         trk.sdf_kernel_us = 0; trk.sdf_queries_J = 0; trk.sdf_queries_noJ = 0
         n_sdf_before = trk.n_sdf_evals
         dfb._lib.CALLS.clear()
+        import gc
+        gc.collect(); gc.disable()                           # no collector pauses inside the ~70 ms timed region
+        sampler.__enter__()                                  # sampling thread up before the clock starts (its start-up costs ms)
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wall0 = time.perf_counter()
         trace = os.environ.get("BENCH_TRACE") == "1"
         marks = []
+        sampler.rows.clear()                                 # keep only samples taken inside the timed region
         t0.record()
-        with sampler as cs:
+        cs = sampler
+        try:
             nxt = upload(Wm) if e2e else None                                     # inside the timed region
             for i in range(Wm, n_frames):
                 l2_flush.zero_()                                                  # cold L2 for every frame
@@ -253,6 +270,9 @@ def run_ours(args):
                     ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append((ev, time.perf_counter()))
             t1.record()
             barrier()
+        finally:
+            sampler.__exit__(None, None, None)
+        gc.enable()
         if trace:
             prev, prev_w = t0, wall0
             per = []

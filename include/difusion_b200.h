@@ -74,6 +74,10 @@ int dfb_get_encoder_engine(void);
 int dfb_ingest_frame(const uint16_t* depth_raw, const uint8_t* color_raw, int H, int W, float depth_scale, int div_mode,
                      float cut_min, float cut_max, int bgr, float* depth_out, float* rgb_out, void* stream);
 
+/* Isometry @ points and rotation @ normals (utils/motion_util.py:323-328, main.py:83-84): out[i] = R xyz[i] (+ t), fp32,
+ * h_R row-major 3x3 on the host, h_t may be NULL (rotation only). */
+int dfb_transform_points(const float* xyz, int n, const float* h_R, const float* h_t, float* out, void* stream);
+
 int dfb_unproject_depth(const float* depth, int H, int W, float fx, float fy, float cx, float cy, float* pc,
                         void* stream);
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "dfb_set_encoder_engine": (_I, [_I]),
     "dfb_get_encoder_engine": (_I, []),
     "dfb_ingest_frame": (_I, [_P, _P, _I, _I, _F, _I, _F, _F, _I, _P, _P, _P]),
+    "dfb_transform_points": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "dfb_unproject_depth": (_I, [_P, _I, _I, _F, _F, _F, _F, _P, _P]),
     "dfb_pcproc_ws_bytes": (_SZ, [_I]),
     "dfb_remove_radius_outlier": (_I, [_P, _I, _I, _F, _P, _P, _SZ, _P]),
@@ -85,7 +86,7 @@ SIGNATURES = {
 
 # kernels (and memset nodes excluded) each entry point launches; used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
-    "dfb_ingest_frame": 1, "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 6,
+    "dfb_ingest_frame": 1, "dfb_transform_points": 1, "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 6,
     "dfb_point_box_filter": 14, "dfb_preprocess_frame": 45, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
     "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,

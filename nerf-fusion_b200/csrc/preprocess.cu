@@ -32,6 +32,23 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
   pc[3 * i + 2] = z;
 }
 
+// Isometry @ points (utils/motion_util.py:323-328: other @ R^T + t in fp32).  A 3x3 transform does not need cuBLAS -- and
+// must not use it in the frame loop: a point count cuBLAS has not seen before can select a kernel that is not loaded
+// yet, and the lazy module load was measured at 20-36 ms in the middle of a 1.1 ms frame.
+struct Rt9 { float r[9], t[3]; };
+__global__ void __launch_bounds__(256) transform_points_kernel(const float* __restrict__ xyz, int n, Rt9 R, bool add_t, float* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float acc = x * R.r[3 * a];
+    acc = fmaf(y, R.r[3 * a + 1], acc);
+    acc = fmaf(z, R.r[3 * a + 2], acc);
+    out[3 * (size_t)i + a] = add_t ? __fadd_rn(acc, R.t[a]) : acc;
+  }
+}
+
 // Frame ingest (dataset/production/icl_nuim.py:110-114 + main.py:56-57): the raw 16-bit depth PNG and 8-bit colour image are
 // uploaded as they are (5 bytes/pixel instead of 16) and converted here: depth = raw / scale, colour = raw / 255, optional
 // BGR -> RGB swap (cv2.cvtColor in the reference), optional clipping to NaN outside [cut_min, cut_max].
@@ -624,6 +641,18 @@ int dfb_remove_radius_outlier(const float* pc4, int n, int nb_points, float radi
   int rc = build_grid(pc4, n, radius, GRID_CAP_COARSE, w, s);
   if (rc) return rc;
   radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, radius, mask, nullptr);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_transform_points(const float* xyz, int n, const float* h_R, const float* h_t, float* out, void* stream) {
+  DFB_CHECK_ARG(n >= 0 && h_R, "transform_points");
+  if (n == 0) return DFB_OK;
+  DFB_CHECK_ARG(xyz && out, "transform_points: null pointer");
+  Rt9 R;
+  for (int i = 0; i < 9; ++i) R.r[i] = h_R[i];
+  for (int i = 0; i < 3; ++i) R.t[i] = h_t ? h_t[i] : 0.f;
+  transform_points_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(xyz, n, R, h_t != nullptr, out);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -8,6 +8,7 @@ streams); all arithmetic happens in libdifusion_b200.so.  There is no CPU path.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -79,6 +80,17 @@ def ingest_frame(depth_raw=None, color_raw=None, depth_scale=5000.0, depth_cut=N
                                            lo, hi, int(bool(bgr)), _p(depth) if depth is not None else None,
                                            _p(rgb) if rgb is not None else None, _stream()))
     return depth, rgb
+
+
+def transform_points(xyz, R, t=None):
+    """Isometry @ xyz (motion_util.py:323-328): xyz f32[N,3] CUDA, R 3x3 / t (3,) host arrays -> R xyz + t, f32[N,3]."""
+    _chk(xyz, "xyz", torch.float32)
+    out = torch.empty_like(xyz)
+    Rf = fptr(np.asarray(R, dtype=np.float32).reshape(-1).tolist())
+    tf = fptr(np.asarray(t, dtype=np.float32).reshape(-1).tolist()) if t is not None else None
+    with torch.cuda.device(xyz.device):
+        check(_lib.load().dfb_transform_points(_p(xyz), xyz.size(0), Rf, tf, _p(out), _stream()))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- imgproc

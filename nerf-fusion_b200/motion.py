@@ -148,6 +148,10 @@ class Isometry:
     def __matmul__(self, other):
         if hasattr(other, "device"):                      # torch (N,3): other @ R^T + t in fp32 (motion_util.py:323-328)
             assert other.ndim == 2 and other.size(1) == 3
+            import torch
+            if other.is_cuda and other.dtype == torch.float32:
+                from . import ext                          # one small kernel instead of a cuBLAS GEMM + add (see csrc/preprocess.cu)
+                return ext.transform_points(other.contiguous(), self.q.rotation_matrix, self.t)
             R, t = self.torch_matrices(other.device)
             return other @ R.t() + t.unsqueeze(0)
         if isinstance(other, Isometry):

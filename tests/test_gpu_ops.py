@@ -212,3 +212,19 @@ def test_ingest_frame_and_reader(tmp_path):
         assert np.array_equal(fd.depth.cpu().numpy(), od) and np.array_equal(fd.rgb.cpu().numpy(), oc)
         assert np.abs(fd.depth.cpu().numpy() - D[f"f{i}_depth"]).max() < 1e-6          # reciprocal vs IEEE: 1 ulp
         assert np.abs(fd.gt_pose.t - D[f"f{i}_gt_t"]).max() < 1e-12 and fd.calib.dscale == 5000.0
+
+
+def test_transform_points_equals_torch():
+    """Isometry @ cloud through the small kernel == the reference's fp32 `other @ R^T + t` (motion_util.py:323-328) to an ulp
+    or two (cuBLAS may order the three products differently); rotation-only and empty inputs."""
+    d = pkg()
+    rng = np.random.RandomState(3)
+    iso = d.Isometry(q=d.Quaternion(array=[0.3, -0.5, 0.7, 0.2]), t=np.array([1.5, -2.0, 0.25]))
+    x = torch.from_numpy((rng.rand(5001, 3) * 6 - 3).astype(np.float32)).to(DEV)
+    R, t = iso.torch_matrices(DEV)
+    ref = (x.cpu() @ R.cpu().t() + t.cpu().unsqueeze(0)).numpy()
+    out = (iso @ x).cpu().numpy()
+    assert np.abs(out - ref).max() <= 4e-7 * np.abs(ref).max()
+    rot = (iso.rotation @ x).cpu().numpy()
+    assert np.abs(rot - (x.cpu() @ R.cpu().t()).numpy()).max() <= 4e-7 * 6
+    assert (iso @ x[:0]).shape == (0, 3)

@@ -16,16 +16,20 @@ def wrap(obj, name):
     def g(*a, **k):
         t = time.perf_counter(); r = f(*a, **k); T[name] = T.get(name, 0) + (time.perf_counter() - t) * 1e3; return r
     setattr(obj, name, g)
-for rep in range(5):
+for rep in range(8):
     m, trk = bench.make_system(dfb, dev)
     wrap(m, "_inflate_latent_buffer"); wrap(m, "_workspace")
     for i, (d, c) in enumerate(frames):
         l2.zero_()
-        pose = trk.track_camera(c, d, calib, first_iso if i == 0 else None)
+        tt0 = time.perf_counter()
+        pose = trk.track_camera(c, d, calib, first_iso if i == 0 else None, depth_cut=(0.5, 5.0))
+        tt1 = time.perf_counter()
         if i % 20 == 0:
             T.clear()
             pc, nrm = trk.last_processed_pc
+            ta = time.perf_counter()
             a = pose @ pc; b = pose.rotation @ nrm
+            print("rep", rep, "frame", i, "track host ms %.2f, pose @ cloud host ms %.2f" % ((tt1 - tt0) * 1e3, (time.perf_counter() - ta) * 1e3))
             t0 = time.perf_counter()
             m.integrate_keyframe(a, b, do_optimize=False)
             t1 = time.perf_counter()

@@ -55,10 +55,11 @@ _WS = Workspace()
 
 
 # ----------------------------------------------------------------------------------------------- frame ingest
-def ingest_frame(depth_raw=None, color_raw=None, depth_scale=5000.0, depth_cut=None, bgr=False, div_mode=1):
+def ingest_frame(depth_raw=None, color_raw=None, depth_scale=5000.0, depth_cut=None, bgr=False, div_mode=1, out=None):
     """dataset/production/icl_nuim.py:110-114 (+ main.py:56-57 when depth_cut is given) on the device: depth_raw uint16[H,W]
     and / or color_raw uint8[H,W,3] (CUDA copies of the decoded images) -> (depth f32[H,W] | None, rgb f32[H,W,3] | None).
-    div_mode 1 = multiply by the fp32 reciprocal (torch CUDA's tensor / scalar, what the reference runs), 0 = IEEE divide."""
+    div_mode 1 = multiply by the fp32 reciprocal (torch CUDA's tensor / scalar, what the reference runs), 0 = IEEE divide.
+    out = (depth f32[H,W], rgb f32[H,W,3]): optional preallocated outputs (a streaming reader reuses two sets)."""
     ref = depth_raw if depth_raw is not None else color_raw
     if ref is None:
         raise ValueError("ingest_frame needs depth_raw and / or color_raw")
@@ -71,8 +72,13 @@ def ingest_frame(depth_raw=None, color_raw=None, depth_scale=5000.0, depth_cut=N
         if color_raw.dim() != 3 or color_raw.size(2) != 3:
             raise RuntimeError("color_raw must be (H, W, 3)")
     H, W = int(ref.shape[0]), int(ref.shape[1])
-    depth = torch.empty((H, W), dtype=torch.float32, device=ref.device) if depth_raw is not None else None
-    rgb = torch.empty((H, W, 3), dtype=torch.float32, device=ref.device) if color_raw is not None else None
+    depth = rgb = None
+    if depth_raw is not None:
+        depth = out[0] if out is not None else torch.empty((H, W), dtype=torch.float32, device=ref.device)
+        _chk(depth, "out depth", torch.float32)
+    if color_raw is not None:
+        rgb = out[1] if out is not None else torch.empty((H, W, 3), dtype=torch.float32, device=ref.device)
+        _chk(rgb, "out rgb", torch.float32)
     lo, hi = (float(depth_cut[0]), float(depth_cut[1])) if depth_cut is not None else (0.0, 0.0)
     with torch.cuda.device(ref.device):
         check(_lib.load().dfb_ingest_frame(_p(depth_raw) if depth_raw is not None else None,

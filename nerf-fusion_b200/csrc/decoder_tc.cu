@@ -264,6 +264,9 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
 }
 
 // reverse pass: seeds on z and u -> d/d(xyz) in network units (both threads of a row return the full sum)
+// HAS_U = false: the caller's seed on the std head is identically zero (the tracker detaches std, tracker.py:191), so its
+// weights are neither loaded nor multiplied
+template <bool HAS_U = true>
 __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, float g[3]) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const int row = c.row;
@@ -278,13 +281,14 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
     const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W3X + 3 * col0);
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 wz = w4[i4], wv = wu[i4];
+      const float4 wz = w4[i4];
+      const float4 wv = HAS_U ? wu[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 ta = t4[3 * i4], tb = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];     // taps of 4 consecutive units, 3 floats each
       const uint32_t mm = m >> (4 * i4);
-      const float d0 = (mm & 1u) ? fmaf(seed_z, wz.x, seed_u * wv.x) : 0.f;
-      const float d1 = (mm & 2u) ? fmaf(seed_z, wz.y, seed_u * wv.y) : 0.f;
-      const float d2 = (mm & 4u) ? fmaf(seed_z, wz.z, seed_u * wv.z) : 0.f;
-      const float d3 = (mm & 8u) ? fmaf(seed_z, wz.w, seed_u * wv.w) : 0.f;
+      const float d0 = (mm & 1u) ? (HAS_U ? fmaf(seed_z, wz.x, seed_u * wv.x) : seed_z * wz.x) : 0.f;
+      const float d1 = (mm & 2u) ? (HAS_U ? fmaf(seed_z, wz.y, seed_u * wv.y) : seed_z * wz.y) : 0.f;
+      const float d2 = (mm & 4u) ? (HAS_U ? fmaf(seed_z, wz.z, seed_u * wv.z) : seed_z * wz.z) : 0.f;
+      const float d3 = (mm & 8u) ? (HAS_U ? fmaf(seed_z, wz.w, seed_u * wv.w) : seed_z * wz.w) : 0.f;
       d[4 * i4] = d0; d[4 * i4 + 1] = d1; d[4 * i4 + 2] = d2; d[4 * i4 + 3] = d3;
       ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
       ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb.x, d1, ga[1]); ga[2] = fmaf(tb.y, d1, ga[2]);
@@ -502,7 +506,7 @@ __device__ __forceinline__ void sdf_tiles(Ctx& c, const MapDev& M, const PoseDev
     float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (with_J) {
       float g[3];
-      backward(c, valid ? (1.0f - s * s) / sd : 0.f, 0.f, g);
+      backward<false>(c, valid ? (1.0f - s * s) / sd : 0.f, 0.f, g);
       if (valid) {
         float gw[3];
 #pragma unroll

@@ -66,7 +66,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
   volatile GnRecord* hring = reinterpret_cast<volatile GnRecord*>(h_pinned);
   for (int i = 0; i < 4; ++i) { hring[i].seq = 0; hring[i].check = 0; }
 
-  static std::vector<cudaEvent_t> events;                           // pairs, grown on demand (timing only)
+  static thread_local std::vector<cudaEvent_t> events;                           // pairs, grown on demand (timing only)
   auto event = [&](size_t i) -> cudaEvent_t {
     while (events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
     return events[i];
@@ -80,7 +80,7 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
   const float intr4[4] = {(float)init.intr[0], (float)init.intr[1], (float)init.intr[2], (float)init.intr[3]};
 
   const bool tc_engine = dfb_get_decoder_engine() == 1;
-  static int seq_base = 0;                                          // records carry a process-unique, non-zero sequence number
+  static thread_local int seq_base = 0;                             // (per host thread: two trackers may solve concurrently)                                          // records carry a process-unique, non-zero sequence number
   struct Slot { int seq, gi, step, sdf_event; };
   int n_sdf = 0, n_rgb = 0, n_launches = 1 /* gn_init_kernel */, i_iter = 0, n_events = 0, error = 0;
   double sdf_ms = 0.0, sdf_q_j = 0.0, sdf_q_nj = 0.0;

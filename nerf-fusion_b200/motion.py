@@ -146,7 +146,9 @@ class Isometry:
         return (torch.from_numpy(self.q.rotation_matrix).to(device).float(), torch.from_numpy(self.t).to(device).float())
 
     def __matmul__(self, other):
-        if hasattr(other, "device"):                      # torch (N,3): other @ R^T + t in fp32 (motion_util.py:323-328)
+        # torch (N,3): other @ R^T + t in fp32 (motion_util.py:323-328).  The reference tests hasattr(other, "device"), which
+        # numpy >= 2 arrays also have; is_cuda is torch-only.
+        if hasattr(other, "is_cuda"):
             assert other.ndim == 2 and other.size(1) == 3
             import torch
             if other.is_cuda and other.dtype == torch.float32:

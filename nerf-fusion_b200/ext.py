@@ -238,10 +238,12 @@ def point_box_filter(points, normals, voxel_size, div_mode=0):
 
 
 def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, max_nn=16, normal_radius=0.1,
-                     cam_xyz=(0.0, 0.0, 0.0), box_voxel=0.02, div_mode=0, sync=True):
+                     cam_xyz=(0.0, 0.0, 0.0), box_voxel=0.02, div_mode=0, sync=True, ws=None):
     """tracker.py:89-120 (geometry half) fused: full-resolution depth (H,W) with NaN = invalid and its intrinsics ->
     (points (N,3), normals (N,3)) in camera space.  One device->host read (the row count).
-    sync=False: no host read (CUDA-graph capturable); returns (points (n_max,3), normals (n_max,3), count i32[1])."""
+    sync=False: no host read (CUDA-graph capturable); returns (points (n_max,3), normals (n_max,3), count i32[1]).
+    ws: caller-owned workspace (uint8, >= dfb_preprocess_ws_bytes(H, W)).  A captured graph bakes the workspace address in,
+    so it must not be the shared growable buffer, which is released whenever a later call needs a bigger one."""
     _chk(depth, "depth", torch.float32)
     H, W = depth.shape
     dev = depth.device
@@ -250,7 +252,10 @@ def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, m
     out_n = torch.empty((n_max, 3), dtype=torch.float32, device=dev)
     cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
     lib = _lib.load()
-    ws = _WS.get(dev, lib.dfb_preprocess_ws_bytes(H, W))
+    if ws is None:
+        ws = _WS.get(dev, lib.dfb_preprocess_ws_bytes(H, W))
+    elif ws.numel() < lib.dfb_preprocess_ws_bytes(H, W) or ws.device != dev:
+        raise RuntimeError("preprocess_frame: workspace too small or on another device")
     with torch.cuda.device(dev):
         check(lib.dfb_preprocess_frame(_p(depth), H, W, fx, fy, cx, cy, int(nb_points), float(outlier_radius), int(max_nn),
                                        float(normal_radius), fptr(cam_xyz), float(box_voxel), int(div_mode), _p(out_p), _p(out_n),

@@ -74,6 +74,7 @@ class SDFTracker:
         # decisions) is captured once per (image size, intrinsics) into a CUDA graph and replayed from static buffers
         self.graph_frontend = True
         self._fe_graphs = {}               # key -> dict(graph, static inputs/outputs)
+        self._fe_ws = {}                   # depth shape -> workspace owned by the front end (its address is baked into the graphs)
         self._fe_seen = {}                 # key -> eager calls so far (the first call warms kernels and workspaces up)
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
@@ -126,8 +127,14 @@ class SDFTracker:
                                      torch.full_like(depth_data, float("nan")), depth_data)
         cur_intensity = torch.mean(rgb_data, dim=-1)
         Is, Ds, Gs = self._make_image_pyramid(cur_intensity, depth_data)
+        # the front end owns its workspace: the captured graphs keep its address (ext.preprocess_frame, `ws`)
+        shape = tuple(Ds[0].shape)
+        ws = self._fe_ws.get(shape)
+        if ws is None:
+            ws = torch.empty(int(self.map.lib.dfb_preprocess_ws_bytes(shape[0], shape[1])) + 1024, dtype=torch.uint8, device=self.map.device)
+            self._fe_ws[shape] = ws
         out_p, out_n, cnt = ext.preprocess_frame(Ds[0].contiguous(), calib.fx, calib.fy, calib.cx, calib.cy, 16, 0.05, 16, 0.1,
-                                                 (0.0, 0.0, 0.0), 0.02, self.map.div_mode, sync=False)
+                                                 (0.0, 0.0, 0.0), 0.02, self.map.div_mode, sync=False, ws=ws)
         return Is, Ds, Gs, out_p, out_n, cnt
 
     def _frontend_graphed(self, rgb_data, depth_data, calib, depth_cut=None):

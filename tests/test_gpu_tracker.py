@@ -173,3 +173,27 @@ def test_pose_parity_on_the_reference_points(weights, T):
         dt = np.abs(pose.t - T[f"f{i}_pose_t"]).max(); dR = np.abs(pose.q.rotation_matrix - T[f"f{i}_pose_R"]).max()
         print("frame", i, "pose vs reference golden: t %.2e R %.2e" % (dt, dR))
         assert dt < 1e-5 and dR < 1e-5
+
+
+def test_graph_front_end_survives_workspace_growth(weights, T):
+    """The captured front end owns its workspace: another op that makes the shared growable workspace reallocate (here a
+    large decode_cubes, as extract_mesh does after a keyframe) must not leave the graphs pointing at freed memory."""
+    d = pkg()
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    m = make_map(weights)
+    trk = d.SDFTracker(m, ns(TRACKING))
+    rgb, depth = _frame(T, 0)
+    ref = None
+    for rep in range(5):
+        out = trk._frontend_graphed(rgb, depth, calib, None)
+        torch.cuda.synchronize()
+        n = int(out[5].item())
+        cur = (out[3][:n].clone(), out[4][:n].clone())
+        if ref is None:
+            ref = cur
+        assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
+        if rep == 2:                                                 # graphs exist now: grow the shared workspace and scribble over the old one
+            big = d.ext._WS.get(torch.device(DEV), 64 << 20)
+            big.fill_(0xAB)
+            junk = [torch.full((1 << 22,), 0xCD, dtype=torch.uint8, device=DEV) for _ in range(8)]
+            del junk

@@ -1,0 +1,56 @@
+"""The CPU oracle (oracle/map_oracle.py, oracle/tracker_oracle.py) against the golden vectors the REFERENCE's own code produced
+(oracle/make_golden.py ran /root/reference/system/map.py and tracker.py on these inputs): this is what pins the checker the
+GPU parity tests lean on."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tracker_oracle as TO
+from util import GOLD, make_oracle_map, pkg
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(GOLD / "map_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def W():
+    return pkg().weights.load_npz(GOLD / "weights.npz")
+
+
+@pytest.fixture(scope="module")
+def omap(W, G):
+    om = make_oracle_map(W)
+    Pw, Nw = torch.from_numpy(G["Pw"]), torch.from_numpy(G["Nw"])
+    m1 = om.integrate_keyframe(Pw, Nw)
+    s1 = dict(mask=m1.numpy().copy(), n=om.n_occupied, pos=om.latent_vecs_pos[:om.n_occupied].numpy().copy(),
+              cnt=om.voxel_obs_count[:om.n_occupied].numpy().copy(), lat=om.latent_vecs[:om.n_occupied].numpy().copy(),
+              cap=om.latent_vecs.size(0))
+    m2 = om.integrate_keyframe(Pw + torch.from_numpy(G["k2_shift"]), Nw)
+    return om, s1, m2
+
+
+def test_oracle_integrate_matches_reference_golden(omap, G):
+    om, s1, m2 = omap
+    assert np.array_equal(s1["mask"], G["k1_mask"]) and s1["n"] == int(G["k1_n_occupied"]) and s1["cap"] == int(G["k1_capacity"])
+    assert np.array_equal(s1["pos"], G["k1_pos"]) and np.array_equal(s1["cnt"], G["k1_count"])            # ids, slot order, counts: bit-exact
+    assert np.abs(s1["lat"] - G["k1_latent"]).max() <= 1e-5 * np.abs(G["k1_latent"]).max()
+    n = om.n_occupied
+    assert np.array_equal(m2.numpy(), G["k2_mask"]) and n == int(G["k2_n_occupied"])
+    assert np.array_equal(om.latent_vecs_pos[:n].numpy(), G["k2_pos"]) and np.array_equal(om.voxel_obs_count[:n].numpy(), G["k2_count"])
+    assert np.abs(om.latent_vecs[:n].numpy() - G["k2_latent"]).max() <= 1e-5 * np.abs(G["k2_latent"]).max()
+
+
+def test_oracle_get_sdf_and_hg_match_reference_golden(omap, G):
+    om = omap[0]
+    sdf, std, valid = om.get_sdf(torch.from_numpy(G["q_world"]))
+    assert np.array_equal(valid.numpy(), G["q_valid"])
+    assert np.abs(sdf.detach().numpy() - G["q_sdf"]).max() < 1e-5 and np.abs(std.detach().numpy() - G["q_std"]).max() < 1e-5
+    last = TO.Pose(TO.Quaternion(matrix=G["hg_last_R"]), G["hg_last_t"]); delta = TO.Pose(TO.Quaternion(matrix=G["hg_delta_R"]), G["hg_delta_t"])
+    H, g, e, _ = TO.compute_sdf_Hg(om, last, delta, torch.from_numpy(G["Pc"]))
+    # fp32 sums over 12 148 rows in a different order than the reference's einsum: 3e-5 measured
+    assert np.abs(H - G["hg_H"]).max() <= 1e-4 * np.abs(G["hg_H"]).max() and np.abs(g - G["hg_g"]).max() <= 1e-4 * np.abs(G["hg_g"]).max()
+    assert abs(e - float(G["hg_e"])) <= 1e-5 * abs(float(G["hg_e"]))
+    _, _, e_ng, _ = TO.compute_sdf_Hg(om, last, delta, torch.from_numpy(G["Pc"]), no_grad=True)
+    assert abs(e_ng - float(G["hg_e_nograd"])) <= 1e-5 * abs(float(G["hg_e_nograd"]))

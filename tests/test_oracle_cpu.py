@@ -83,3 +83,25 @@ def test_oracle_tracking_matches_reference_golden(W):
     pose, n_eval, _ = TO.gauss_newton(om, pose0, pose0, torch.from_numpy(T["f1_pc"]), cfg, rgb=dict(state=(I0, D0), cur=(I1, D1, G1), K4=K4))
     assert n_eval > 0
     assert np.abs(pose.t - T["f1_pose_t"]).max() < 1e-5 and np.abs(pose.R - T["f1_pose_R"]).max() < 1e-5      # measured 1e-7
+
+
+def test_oracle_meshing_matches_reference_golden(omap, G):
+    """Voxel selection, cube decoding (low pass, trilinear upsampling, refined band) and sparse marching cubes with std-weighted
+    blending against what the reference's extract_mesh produced (its marching cubes ran through the oracle's restatement of
+    mc_interp_kernel.cu inside the reference's own do_meshing)."""
+    from oracle import ops
+    from util import match_rows
+    om = omap[0]
+    focused, occ, mapping = om.meshing_batch(torch.from_numpy(G["k2_updated"]))
+    assert np.array_equal(focused.numpy(), G["mesh_valid_blocks"]) and occ.numel() == int(G["mesh_B"])
+    assert np.array_equal(mapping.numpy(), G["mesh_mapping"])
+    cs, cd = om.decode_cubes(occ, 4)
+    head = G["mesh_cube_sdf_head"].shape[0]
+    assert np.abs(cs[:head].numpy() - G["mesh_cube_sdf_head"]).max() < 1e-5 and np.abs(cd[:head].numpy() - G["mesh_cube_std_head"]).max() < 1e-5
+    assert np.abs(cs.numpy().astype(np.float64).sum(axis=(1, 2, 3)) - G["mesh_cube_sdf_sum"]).max() < 2e-3
+    tri, fid, tstd = ops.marching_cubes_sparse_interp(om.indexer.view(*om.n_xyz).numpy(), focused[:48].numpy(), mapping.numpy(), cs.numpy(),
+                                                      cd.numpy(), int(4e6), om.n_xyz, 0.15)
+    tri_m = tri * np.float32(0.1) + om.bound_min.numpy()
+    assert tri_m.shape == G["mesh_tri_first48"].shape
+    match_rows(tri_m, G["mesh_tri_first48"], 1e-5)
+    assert set(np.unique(fid).tolist()) <= set(G["mesh_valid_blocks"][:48].tolist())

@@ -4,7 +4,6 @@ Follows /root/reference/system/map.py (DenseIndexedMap): state (map.py:199-211),
 integrate_keyframe (:341-453, do_optimize=False path), get_sdf (:560-580), do_meshing sampling (:625-688).
 torch-CPU fp32/int64 so integer results are bit-comparable and float results follow the same op order.
 """
-import math
 
 import numpy as np
 import torch

@@ -1,7 +1,9 @@
 // tcgen05 decoder engine (sm_100a): the 5-layer decoder MLP, its reverse pass and the tracker reduction with the
 // weights RESIDENT in shared memory (one bulk-TMA load per CTA), activations as FP16 K-major SWIZZLE_128B tiles,
-// FP32 accumulators in TMEM, one elected thread issuing tcgen05.mma, 128 threads (one per query row = one TMEM lane)
-// running the epilogues (bias/ReLU/mask -> FP16 -> swizzled smem) between layers.
+// FP32 accumulators in TMEM, one elected thread issuing tcgen05.mma, NPART x 128 threads per tile (NPART threads per
+// query row = TMEM lane, each owning 128 / NPART accumulator columns) running the epilogues (bias/ReLU/mask -> FP16 ->
+// swizzled smem) between layers, GROUPS tiles in flight per CTA.  The file also holds gn_eval_kernel: one Gauss-Newton
+// evaluation (SDF term on these tiles + photometric pixels + block reduction + last-block step) in a single launch.
 //
 //   forward   D[128 x N] = A[128 x K] * W^T      A: activations (K-major), B: weight image (K-major)
 //   reverse   D[128 x K] = delta[128 x N] * W    A: deltas (K-major),      B: the SAME weight image read MN-major
@@ -21,7 +23,7 @@ namespace dfb {
 namespace tc {
 using namespace tcp;
 
-constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 warps, smem tiles, TMEM columns, barrier)
+constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 x NPART warps, smem tiles, TMEM columns, barrier)
 constexpr int NPART = 2;        // threads per row: part p owns accumulator columns [CW p, CW p + CW) (warps 4p..4p+3 of the group; same TMEM
                                 // lanes).  Measured on B200 at 2^24 queries: NPART=2 1.42 G q/s, NPART=4 1.14 G q/s (barrier + redundant
                                 // front-end cost outweighs the extra warps)

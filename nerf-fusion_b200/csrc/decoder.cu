@@ -268,7 +268,7 @@ int dfb::decoder_engine() {
   }
   return g_engine;
 }
-constexpr int TC_BLOB_BYTES = 122880 + 6144;   // decoder_tc.cu: tc::BLOB_BYTES
+constexpr int TC_BLOB_BYTES = 196608 + 6144;   // decoder_tc.cu: tc::BLOB_BYTES
 static inline const void* tc_part(const float* blob) { return blob + DB_TOTAL; }
 
 extern "C" {

@@ -1,15 +1,21 @@
 // tcgen05 decoder engine (sm_100a): the 5-layer decoder MLP, its reverse pass and the tracker reduction with the
-// weights RESIDENT in shared memory (one bulk-TMA load per CTA), activations as FP16 K-major SWIZZLE_128B tiles,
-// FP32 accumulators in TMEM, one elected thread issuing tcgen05.mma, NPART x 128 threads per tile (NPART threads per
-// query row = TMEM lane, each owning 128 / NPART accumulator columns) running the epilogues (bias/ReLU/mask -> FP16 ->
-// swizzled smem) between layers, GROUPS tiles in flight per CTA.  The file also holds gn_eval_kernel: one Gauss-Newton
-// evaluation (SDF term on these tiles + photometric pixels + block reduction + last-block step) in a single launch.
+// weights RESIDENT in shared memory (bulk-TMA loads, one mbarrier per layer) and the ACTIVATIONS RESIDENT IN TENSOR
+// MEMORY: every layer is  D[tmem] = A[tmem] * B[smem]  (tcgen05.mma with the A operand read from TMEM), the epilogue
+// warps read the FP32 accumulator with tcgen05.ld, apply bias / ReLU / mask and write the next layer's A operand back
+// with tcgen05.st -- no shared-memory round trip, no swizzled stores, no proxy fence between layers.
 //
-//   forward   D[128 x N] = A[128 x K] * W^T      A: activations (K-major), B: weight image (K-major)
-//   reverse   D[128 x K] = delta[128 x N] * W    A: deltas (K-major),      B: the SAME weight image read MN-major
+// Accuracy: every product runs as THREE FP16 MMAs into the same FP32 accumulator,
+//     A W  ~=  A_hi W_hi + A_lo W_hi + A_hi W_lo        (x_hi = fp16(x), x_lo = fp16(x - x_hi): 22 significant bits)
+// for activations, deltas AND weights, so the engine agrees with an FP32 evaluation to ~1e-6 (the dropped A_lo W_lo
+// term is 2^-22 relative); this is what lets the default engine meet the north-star tolerances (H, g 1e-4; pose 1e-5).
 //
-// so one FP16 image per layer serves both passes (120 KB for the whole network).  Inputs are split hi+lo into the
-// two halves of the 64-wide input block (weights duplicated) so positions/latents enter with ~22 significant bits.
+//   forward   D[128 x N] = A[128 x K] * W^T      B: weight image read K-major
+//   reverse   D[128 x K] = delta[128 x N] * W    B: the SAME weight image read MN-major
+//
+// One persistent CTA per SM, GROUPS tiles in flight (each: NPART x 128 threads, NPART threads per query row = TMEM lane,
+// 256 TMEM columns: 128 accumulator + 64 A_hi + 64 A_lo), one elected thread per group issuing the MMAs.  The file
+// also holds gn_eval_kernel: one Gauss-Newton evaluation (SDF term on these tiles + photometric pixels + block
+// reduction + last-block step) in a single launch.
 // Math: network/di_decoder.py:55-86; reverse pass: SURVEY.md Appendix B.
 #include <algorithm>
 
@@ -23,59 +29,90 @@ namespace dfb {
 namespace tc {
 using namespace tcp;
 
-constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 x NPART warps, smem tiles, TMEM columns, barrier)
-constexpr int NPART = 2;        // threads per row: part p owns accumulator columns [CW p, CW p + CW) (warps 4p..4p+3 of the group; same TMEM
-                                // lanes).  Measured on B200 at 2^24 queries: NPART=2 1.42 G q/s, NPART=4 1.14 G q/s (barrier + redundant
-                                // front-end cost outweighs the extra warps)
+constexpr int GROUPS = 2;       // tiles in flight per CTA (each with its own 4 x NPART warps, TMEM columns, barrier)
+constexpr int NPART = 2;        // threads per row: part p owns accumulator columns [CW p, CW p + CW) (warps 4p..4p+3 of the group; same TMEM lanes)
 constexpr int CW = 128 / NPART; // accumulator columns per thread
 constexpr int GT = T * NPART;   // threads per tile group
 constexpr int CTA_T = GT * GROUPS;
-// ---- blob (bytes): FP16 swizzled images + FP32 small block; packed by weights.pack_decoder_tc -------------------
-constexpr int IMG_W0 = 0;          // [128 rows x 64]: cols 0..31 = W0, cols 32..63 = W0 again (lo halves of the input)
-constexpr int IMG_W1 = 16384;      // 2 blocks x [128 x 64]
-constexpr int IMG_W2 = 49152;      // 2 blocks x [ 96 x 64]
-constexpr int IMG_W3A = 73728;     // 2 blocks x [128 x 64]: W3[:, 0:96], cols 96..127 zero
-constexpr int IMG_W3B = 106496;    // [128 x 64]: W3[:, 96:128] twice (hi, lo)
-constexpr int IMG_END = 122880;
+// ---- blob (bytes): FP16 SWIZZLE_128B K-major images (64-column blocks of [rows x 128 B]) + FP32 small block;
+//      packed by weights.pack_decoder_tc ----------------------------------------------------------------------------
+constexpr int IMG_W0 = 0;          // [128 x 64]: cols 0..31 = hi(W0), cols 32..63 = lo(W0)
+constexpr int IMG_W1H = 16384;     // 2 blocks x [128 x 64]
+constexpr int IMG_W1L = 49152;
+constexpr int IMG_W2H = 81920;     // 2 blocks x [ 96 x 64]
+constexpr int IMG_W2L = 106496;
+constexpr int IMG_W3H = 131072;    // 2 blocks x [128 x 64]: W3 = [hidden 0..95 | input 96..127]
+constexpr int IMG_W3L = 163840;
+constexpr int IMG_END = 196608;
 constexpr int SMALL_BYTES = 6144;
 constexpr int BLOB_BYTES = IMG_END + SMALL_BYTES;
+static_assert(BLOB_BYTES == 202752, "decoder.cu TC_BLOB_BYTES / weights.pack_decoder_tc");
 // ---- shared memory (bytes from the 1024-aligned base) ------------------------------------------------------------
 constexpr int SM_SMALL = IMG_END;
-constexpr int SM_A = SM_SMALL + SMALL_BYTES;   // 129024 = 126 * 1024: activation tile, 2 blocks x [128 x 64] fp16
-constexpr int SM_XOFF = 32768;                 // input tile [128 x 64] fp16 (hi | lo), after the activation tile
-constexpr int SM_TILE_BYTES = 32768 + 16384;   // per tile group
-constexpr int SM_BAR = SM_A + GROUPS * SM_TILE_BYTES;   // mbarriers + TMEM slot
-constexpr int SM_TOTAL = SM_BAR + 64;
-constexpr int SM_ALLOC = SM_TOTAL + 1024;      // slack for manual 1024-byte alignment
-constexpr int TMEM_COLS = 128 * GROUPS;
+constexpr int SM_EX = SM_SMALL + SMALL_BYTES;           // per group: NPART x 128 rows x 4 floats (row-partner exchange)
+constexpr int SM_EX_BYTES = NPART * T * 4 * 4;
+constexpr int SM_BAR = SM_EX + GROUPS * SM_EX_BYTES;    // mbarriers + TMEM slot + small per-group words
+constexpr int SM_TOTAL = SM_BAR + 128;
+constexpr int SM_ALLOC = SM_TOTAL + 1024;               // slack for manual 1024-byte alignment
+static_assert(SM_ALLOC <= 232448, "shared memory budget");
+// ---- tensor memory: 256 columns per group ---------------------------------------------------------------------
+constexpr int TM_D = 0;            // FP32 accumulator, 128 columns
+constexpr int TM_AH = 128;         // A operand, hi halves: K elements 2c, 2c+1 packed in column c (64 columns = K 128)
+constexpr int TM_AL = 192;         // A operand, lo halves
+constexpr int TM_XK = 96;          // the 32 network inputs sit at K 96..127 of the A operand (= layer 3's [h2 | x] layout)
+constexpr int TMEM_COLS = 256 * GROUPS;
+static_assert(TMEM_COLS <= 512, "tensor memory budget");
+constexpr int NWBAR = 4;           // weight barriers: [0] small + W0, [1] W1, [2] W2, [3] W3
 
 struct Ctx {
   uint8_t* sm;        // 1024-aligned base (generic)
   uint32_t sa;        // same, shared-window address
-  uint32_t tmem;      // TMEM address of this group's accumulator (lane 0)
+  uint32_t tmem;      // TMEM address of this group's columns (lane 0)
   uint32_t tmem_base; // allocation base
   int row, part, grp; // row within the tile (= TMEM lane), column part owned by this thread, tile group
-  uint32_t a_off, x_off;   // byte offsets of this group's activation / input tiles
+  uint32_t ex_off;    // byte offset of this group's exchange scratch
   uint32_t mma_bar;   // shared address of the "MMA done" barrier
-  uint32_t wbar;      // shared address of the "weights landed" barrier (completes once)
-  uint32_t phase;     // its parity
+  uint32_t wbar;      // shared address of the first "weights landed" barrier (each completes once)
+  uint32_t phase;     // parity of mma_bar
   uint32_t mask[4][CW / 32];   // ReLU masks of this thread's columns, per layer
+  uint32_t xh[8], xl[8];       // this thread's half of the packed network inputs (hi / lo), re-staged for layer 3
 };
 
-// Issuing thread only.  K-major A (activation tile at a_addr, blocks of 16 KB), B = weight image at b_addr with B_ROWS rows
-// per 64-column block.  fwd: B read K-major; bwd: the same image read MN-major (k-step s = image rows 16s..16s+15).
-// Everything but the two base addresses is a compile-time constant, so each step is two 64-bit adds and one tcgen05.mma.
-template <int KSTEPS, int N, bool BWD, int B_ROWS>
-__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr, bool accumulate_first) {
+// tcgen05.mma, A operand from tensor memory (cute SM100_MMA_F16BF16_TS)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Issuing thread only.  A = KSTEPS x 8 TMEM columns from a_tmem (K-major, 16 elements per step), B = weight image at b_addr
+// with B_ROWS rows per 64-column block, starting at K step B_S0 of the image.  fwd: B read K-major; bwd: the same image read
+// MN-major (k-step s = image rows 16s..16s+15).  Everything but the base addresses is a compile-time constant.
+template <int KSTEPS, int N, bool BWD, int B_ROWS, int B_S0 = 0>
+__device__ __forceinline__ void issue(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool accumulate_first) {
   constexpr uint32_t idesc = (1u << 4) | ((BWD ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
-  const uint64_t ad0 = smem_desc(a_addr, 16, 1024);
   const uint64_t bd0 = BWD ? smem_desc(b_addr, (uint32_t)B_ROWS * 128u, 1024) : smem_desc(b_addr, 16, 1024);
 #pragma unroll
   for (int s = 0; s < KSTEPS; ++s) {
-    const uint64_t ad = ad0 + (uint64_t)(((s >> 2) * 16384 + (s & 3) * 32) >> 4);
-    const uint64_t bd = bd0 + (uint64_t)((BWD ? s * 2048 : (s >> 2) * (B_ROWS * 128) + (s & 3) * 32) >> 4);
-    mma_f16(c.tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    const int sb = s + B_S0;
+    const uint64_t bd = bd0 + (uint64_t)((BWD ? sb * 2048 : (sb >> 2) * (B_ROWS * 128) + (sb & 3) * 32) >> 4);
+    mma_f16_ts(d_tmem, a_tmem + 8u * s, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
   }
+}
+// one layer = three FP16 products into the same accumulator: A_hi W_hi + A_lo W_hi + A_hi W_lo
+template <int KSTEPS, int N, bool BWD, int B_ROWS>
+__device__ __forceinline__ void issue3(const Ctx& c, int k0, uint32_t img_hi, uint32_t img_lo) {
+  const uint32_t d = c.tmem + TM_D, ah = c.tmem + TM_AH + (k0 >> 1), al = c.tmem + TM_AL + (k0 >> 1);
+  issue<KSTEPS, N, BWD, B_ROWS>(d, ah, c.sa + img_hi, false);
+  issue<KSTEPS, N, BWD, B_ROWS>(d, al, c.sa + img_hi, true);
+  issue<KSTEPS, N, BWD, B_ROWS>(d, ah, c.sa + img_lo, true);
+}
+
+// layer 0: the 32 inputs sit at K 96..127 of the A operand; W0's image holds hi (k-steps 0, 1) and lo (k-steps 2, 3)
+__device__ __forceinline__ void issue_l0(const Ctx& c) {
+  const uint32_t d = c.tmem + TM_D, ah = c.tmem + TM_AH + (TM_XK >> 1), al = c.tmem + TM_AL + (TM_XK >> 1);
+  issue<2, 128, false, 128, 0>(d, ah, c.sa + IMG_W0, false);
+  issue<2, 128, false, 128, 0>(d, al, c.sa + IMG_W0, true);
+  issue<2, 128, false, 128, 2>(d, ah, c.sa + IMG_W0, true);
 }
 
 #ifdef DFB_TC_PROFILE
@@ -105,11 +142,12 @@ __device__ __forceinline__ long long tile_of(const Ctx& c, long long n, long lon
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
 
-// all threads of the group: make the tile writes visible to the tensor core, then thread 0 issues; everyone waits for completion
+// all threads of the group: their tcgen05.st of the next A operand have completed and are ordered before the barrier; thread 0
+// issues the layer's MMAs and commits; everyone waits for completion
 #define TC_LAYER(ISSUE_STMTS)                         \
   do {                                                \
     PROF_MARK(c);                                     \
-    fence_proxy_async();                              \
+    tmem_st_wait();                                   \
     tc_fence_before();                                \
     group_sync(c.grp);                                \
     PROF_MARK(c);                                     \
@@ -125,32 +163,42 @@ __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0,
     PROF_MARK(c);                                     \
   } while (0)
 
-// store 32 consecutive columns [col0, col0+32) of this thread's row into a swizzled K-major tile
-__device__ __forceinline__ void store_cols32(uint8_t* tile, int row, int col0, const float* h) {
+// this thread's TMEM lane: lanes 32 (warp % 4) .. + 31 are the only ones a warp may touch
+__device__ __forceinline__ uint32_t lane_base(const Ctx& c) { return c.tmem + ((uint32_t)(c.row & ~31) << 16); }
+
+// 32 consecutive values of this thread's row -> hi / lo FP16 pairs -> the A operand at K index k0 .. k0 + 31
+__device__ __forceinline__ void store_a32(const Ctx& c, int k0, const float* h) {
+  const uint32_t tb = lane_base(c) + (uint32_t)(k0 >> 1);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int chunk = (col0 >> 3) + q;   // 16-byte chunk index along K
-    uint4 v;
-    v.x = pack_h2(h[8 * q + 0], h[8 * q + 1]); v.y = pack_h2(h[8 * q + 2], h[8 * q + 3]);
-    v.z = pack_h2(h[8 * q + 4], h[8 * q + 5]); v.w = pack_h2(h[8 * q + 6], h[8 * q + 7]);
-    *reinterpret_cast<uint4*>(tile + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+  for (int half = 0; half < 2; ++half) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split_h2(h[16 * half + 2 * q], h[16 * half + 2 * q + 1], hi[q], lo[q]);
+    tmem_st8(tb + TM_AH + 8 * half, hi);
+    tmem_st8(tb + TM_AL + 8 * half, lo);
   }
 }
 
-// hidden-layer forward epilogue for this thread's column half: a = D + b, record [a > 0], relu(a) -> FP16 activation tile
+// the network inputs of this thread's half (16 of 32), kept packed in registers, -> K 96 + 16 part .. of the A operand
+__device__ __forceinline__ void store_x(const Ctx& c) {
+  const uint32_t tb = lane_base(c) + (uint32_t)((TM_XK + 16 * c.part) >> 1);
+  tmem_st8(tb + TM_AH, c.xh);
+  tmem_st8(tb + TM_AL, c.xl);
+}
+
+// hidden-layer forward epilogue for this thread's columns: a = D + b, record [a > 0], relu(a) -> A operand (hi | lo)
 template <int NCOLS>
 __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  const int row = c.row;
-  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t tb = lane_base(c) + TM_D;
 #pragma unroll
   for (int jj = 0; jj < CW / 32; ++jj) {
-    const int col0 = CW * c.part + 32 * jj;
-    if (col0 < NCOLS) {                     // warp-uniform
+    const int cb = CW * c.part + 32 * jj;
+    if (cb < NCOLS) {                       // warp-uniform
       float v[32];
-      tmem_ld32(tbase + col0, v);
+      tmem_ld32(tb + cb, v);
       uint32_t m = 0;
-      const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + col0);
+      const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + cb);
 #pragma unroll
       for (int i4 = 0; i4 < 8; ++i4) {
         const float4 b = b4[i4];
@@ -159,33 +207,32 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
         v[4 * i4] = fmaxf(a0, 0.f); v[4 * i4 + 1] = fmaxf(a1, 0.f); v[4 * i4 + 2] = fmaxf(a2, 0.f); v[4 * i4 + 3] = fmaxf(a3, 0.f);
       }
       c.mask[layer][jj] = m;
-      store_cols32(c.sm + c.a_off, row, col0, v);
+      store_a32(c, cb, v);
     }
   }
 }
 
-// reverse epilogue: delta = D * mask[layer] -> FP16 tile
+// reverse epilogue: delta = D * mask[layer] -> A operand (hi | lo)
 template <int NCOLS>
 __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
-  const int row = c.row;
-  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t tb = lane_base(c) + TM_D;
 #pragma unroll
   for (int jj = 0; jj < CW / 32; ++jj) {
-    const int col0 = CW * c.part + 32 * jj;
-    if (col0 < NCOLS) {
+    const int cb = CW * c.part + 32 * jj;
+    if (cb < NCOLS) {
       float v[32];
-      tmem_ld32(tbase + col0, v);
+      tmem_ld32(tb + cb, v);
       const uint32_t m = c.mask[layer][jj];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
-      store_cols32(c.sm + c.a_off, row, col0, v);
+      store_a32(c, cb, v);
     }
   }
 }
 
-// the two threads of a row (column halves) combine partial sums through the (currently idle) input tile
+// the two threads of a row (column halves) combine partial sums through the group's exchange scratch
 __device__ __forceinline__ void exchange(Ctx& c, float* vals, int nvals) {
-  float* ex = reinterpret_cast<float*>(c.sm + c.x_off);
+  float* ex = reinterpret_cast<float*>(c.sm + c.ex_off);
   for (int k = 0; k < nvals; ++k) ex[(c.part * T + c.row) * 4 + k] = vals[k];
   group_sync(c.grp);
   for (int k = 0; k < nvals; ++k) {
@@ -197,58 +244,55 @@ __device__ __forceinline__ void exchange(Ctx& c, float* vals, int nvals) {
   group_sync(c.grp);
 }
 
-// Write this row's query (29 latent + 3 rel) into the input tile [hi(32) | lo(32)]: each of the NPART threads of the row
-// stores XC = 64 / NPART consecutive columns (FP16 hi parts in columns 0..31, x - hi in 32..63).
-constexpr int XC = 64 / NPART;
+// Stage this row's query (29 latent + 3 rel): each of the NPART threads of the row packs XC = 32 / NPART consecutive inputs
+// (hi / lo FP16 pairs, kept in c.xh / c.xl) and writes them to K 96.. of the A operand, where layer 0 reads them.
+constexpr int XC = 32 / NPART;
+static_assert(XC == 16, "xh / xl hold 8 packed pairs");
 __device__ __forceinline__ void store_input(Ctx& c, const float* __restrict__ latent_row, const float rel[3], bool valid) {
-  const int col_begin = XC * c.part;
-  const bool lo = col_begin >= 32;
-  const int k0 = col_begin & 31;
+  const int k0 = XC * c.part;
   float h[XC];
 #pragma unroll
   for (int i = 0; i < XC; ++i) {
     const int k = k0 + i;
     float x = 0.f;
     if (valid) x = k < DFB_LATENT_DIM ? __ldg(latent_row + k) : (k == DFB_LATENT_DIM ? rel[0] : (k == DFB_LATENT_DIM + 1 ? rel[1] : rel[2]));
-    const float hi = __half2float(__float2half_rn(x));
-    h[i] = lo ? x - hi : hi;
+    h[i] = x;
   }
 #pragma unroll
-  for (int q = 0; q < XC / 8; ++q) {
-    const int chunk = (col_begin >> 3) + q;
-    uint4 v;
-    v.x = pack_h2(h[8 * q + 0], h[8 * q + 1]); v.y = pack_h2(h[8 * q + 2], h[8 * q + 3]);
-    v.z = pack_h2(h[8 * q + 4], h[8 * q + 5]); v.w = pack_h2(h[8 * q + 6], h[8 * q + 7]);
-    *reinterpret_cast<uint4*>(c.sm + c.x_off + c.row * 128 + (((chunk & 7) ^ (c.row & 7)) << 4)) = v;
-  }
+  for (int q = 0; q < XC / 2; ++q) split_h2(h[2 * q], h[2 * q + 1], c.xh[q], c.xl[q]);
+  store_x(c);
 }
 
 // forward pass of the tile; returns pre-activation heads z (sdf) and u (std)
 __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  mbar_wait(c.wbar, 0);   // phase 0 completes once (bulk load of the network); later calls return immediately
-  TC_LAYER((issue<4, 128, false, 128>(c, c.sa + c.x_off, c.sa + IMG_W0, false)));
+  // each weight barrier completes once (phase 0); later waits return immediately
+  mbar_wait(c.wbar, 0);
+  TC_LAYER(issue_l0(c));                                                         // layer 0: K = 32 inputs at K 96..127 of the A operand
   epi_fwd<128>(c, 0, DS_B0);
-  TC_LAYER((issue<8, 128, false, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));
+  mbar_wait(c.wbar + 8, 0);
+  TC_LAYER((issue3<8, 128, false, 128>(c, 0, IMG_W1H, IMG_W1L)));
   epi_fwd<128>(c, 1, DS_B1);
-  TC_LAYER((issue<8, 96, false, 96>(c, c.sa + c.a_off, c.sa + IMG_W2, false)));
+  mbar_wait(c.wbar + 16, 0);
+  TC_LAYER((issue3<8, 96, false, 96>(c, 0, IMG_W2H, IMG_W2L)));
   epi_fwd<96>(c, 2, DS_B2);
-  TC_LAYER((issue<8, 128, false, 128>(c, c.sa + c.a_off, c.sa + IMG_W3A, false));
-           (issue<4, 128, false, 128>(c, c.sa + c.x_off, c.sa + IMG_W3B, true)));
+  store_x(c);                                                                    // layer 3 input = [h2 (96) | x (32)]
+  mbar_wait(c.wbar + 24, 0);
+  TC_LAYER((issue3<8, 128, false, 128>(c, 0, IMG_W3H, IMG_W3L)));
   // heads in FP32 straight from the accumulator (h3 never leaves TMEM/registers); each thread sums its 64 columns
-  const int row = c.row;
-  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t tb = lane_base(c) + TM_D;
+  const int col0 = CW * c.part;
   float zu[2] = {0.f, 0.f};
   float z1 = 0.f, u1 = 0.f;
 #pragma unroll
   for (int jj = 0; jj < CW / 32; ++jj) {
-    const int col0 = CW * c.part + 32 * jj;
+    const int cb = col0 + 32 * jj;
     float v[32];
-    tmem_ld32(tbase + col0, v);
+    tmem_ld32(tb + cb, v);
     uint32_t m = 0;
-    const float4* b4 = reinterpret_cast<const float4*>(sm + DS_B3 + col0);
-    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + col0);
-    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + col0);
+    const float4* b4 = reinterpret_cast<const float4*>(sm + DS_B3 + cb);
+    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + cb);
+    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + cb);
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
       const float4 b = b4[i4], wz = w4[i4], wv = wu[i4];
@@ -271,16 +315,16 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
 template <bool HAS_U = true>
 __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, float g[3]) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  const int row = c.row;
+  const int col0 = CW * c.part;
   float ga[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int jj = 0; jj < CW / 32; ++jj) {
-    const int col0 = CW * c.part + 32 * jj;
+    const int cb = col0 + 32 * jj;
     float d[32];
     const uint32_t m = c.mask[3][jj];
-    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + col0);
-    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + col0);
-    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W3X + 3 * col0);
+    const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + cb);
+    const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + cb);
+    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W3X + 3 * cb);
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
       const float4 wz = w4[i4];
@@ -297,30 +341,30 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
       ga[0] = fmaf(tb.z, d2, ga[0]); ga[1] = fmaf(tb.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
       ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
     }
-    store_cols32(c.sm + c.a_off, row, col0, d);
+    store_a32(c, cb, d);
   }
-  TC_LAYER((issue<8, 128, true, 128>(c, c.sa + c.a_off, c.sa + IMG_W3A, false)));   // delta2 = delta3 * W3[:, :96] (cols 96.. are 0)
+  TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W3H, IMG_W3L)));   // D[:, :96] = delta2 = delta3 * W3[:, :96]  (cols 96.. = d/d(input) via the skip, unused here)
   epi_bwd<96>(c, 2);
-  TC_LAYER((issue<6, 128, true, 96>(c, c.sa + c.a_off, c.sa + IMG_W2, false)));     // delta1 = delta2 * W2
+  TC_LAYER((issue3<6, 128, true, 96>(c, 0, IMG_W2H, IMG_W2L)));    // delta1 = delta2 * W2
   epi_bwd<128>(c, 1);
-  TC_LAYER((issue<8, 128, true, 128>(c, c.sa + c.a_off, c.sa + IMG_W1, false)));    // delta0 = delta1 * W1 (masked below)
-  const uint32_t tbase = c.tmem + ((uint32_t)(row & ~31) << 16);
+  TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W1H, IMG_W1L)));   // delta0 = delta1 * W1 (masked below)
+  const uint32_t tb = lane_base(c) + TM_D;
 #pragma unroll
   for (int jj = 0; jj < CW / 32; ++jj) {
-    const int col0 = CW * c.part + 32 * jj;
+    const int cb = col0 + 32 * jj;
     float v[32];
-    tmem_ld32(tbase + col0, v);
+    tmem_ld32(tb + cb, v);
     const uint32_t m = c.mask[0][jj];
-    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * col0);
+    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * cb);
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 ta = t4[3 * i4], tb = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];
+      const float4 ta = t4[3 * i4], tb_ = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];
       const uint32_t mm = m >> (4 * i4);
       const float d0 = (mm & 1u) ? v[4 * i4] : 0.f, d1 = (mm & 2u) ? v[4 * i4 + 1] : 0.f;
       const float d2 = (mm & 4u) ? v[4 * i4 + 2] : 0.f, d3 = (mm & 8u) ? v[4 * i4 + 3] : 0.f;
       ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
-      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb.x, d1, ga[1]); ga[2] = fmaf(tb.y, d1, ga[2]);
-      ga[0] = fmaf(tb.z, d2, ga[0]); ga[1] = fmaf(tb.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
+      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb_.x, d1, ga[1]); ga[2] = fmaf(tb_.y, d1, ga[2]);
+      ga[0] = fmaf(tb_.z, d2, ga[0]); ga[1] = fmaf(tb_.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
       ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
     }
   }
@@ -330,7 +374,8 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
 
 extern __shared__ unsigned char tc_smem_raw[];
 
-// CTA prologue: align, barriers, TMEM, one bulk load of the whole network
+// CTA prologue: align, barriers, TMEM, bulk loads of the network (one barrier per layer, so layer 0 can start as soon as
+// its 22 KB have landed while the other 180 KB are still in flight)
 __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -340,36 +385,39 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   c.grp = threadIdx.x / GT;
   c.part = (threadIdx.x % GT) / T;
   c.row = threadIdx.x % T;
-  c.a_off = SM_A + c.grp * SM_TILE_BYTES;
-  c.x_off = c.a_off + SM_XOFF;
-  const uint32_t wbar = c.sa + SM_BAR, slot = c.sa + SM_BAR + 48;
-  c.mma_bar = c.sa + SM_BAR + 8 + 8 * c.grp;
+  c.ex_off = SM_EX + c.grp * SM_EX_BYTES;
+  const uint32_t wbar = c.sa + SM_BAR, slot = c.sa + SM_BAR + 64;
+  c.mma_bar = c.sa + SM_BAR + 32 + 8 * c.grp;
   if (threadIdx.x == 0) {
-    mbar_init(wbar, 1);
-    for (int g = 0; g < GROUPS; ++g) mbar_init(c.sa + SM_BAR + 8 + 8 * g, 1);
+    for (int l = 0; l < NWBAR; ++l) mbar_init(wbar + 8 * l, 1);
+    for (int g = 0; g < GROUPS; ++g) mbar_init(c.sa + SM_BAR + 32 + 8 * g, 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (threadIdx.x < 32) tmem_alloc(slot, TMEM_COLS);
   if (threadIdx.x == 0) {
-    mbar_expect_tx(wbar, BLOB_BYTES);
     const char* src = reinterpret_cast<const char*>(blob);
-    for (int off = 0; off < BLOB_BYTES; off += 16128) {   // 8 chunks of 16128 B (multiple of 16)
-      const int n = min(16128, BLOB_BYTES - off);
-      bulk_g2s(c.sa + off, src + off, (uint32_t)n, wbar);
+    // [0] small block + W0, [1] W1 hi|lo, [2] W2 hi|lo, [3] W3 hi|lo; copies of at most 8 KB
+    const int seg_off[NWBAR + 1] = {IMG_W0, IMG_W1H, IMG_W2H, IMG_W3H, IMG_END};
+    mbar_expect_tx(wbar, (uint32_t)(IMG_W1H - IMG_W0 + SMALL_BYTES));
+    bulk_g2s(c.sa + SM_SMALL, src + IMG_END, SMALL_BYTES, wbar);
+    for (int l = 0; l < NWBAR; ++l) {
+      if (l > 0) mbar_expect_tx(wbar + 8 * l, (uint32_t)(seg_off[l + 1] - seg_off[l]));
+      for (int off = seg_off[l]; off < seg_off[l + 1]; off += 8192) bulk_g2s(c.sa + off, src + off, 8192u, wbar + 8 * l);
     }
   }
-  // zero the activation / input tiles once (unused K columns must be finite)
-  for (int i = threadIdx.x; i < GROUPS * SM_TILE_BYTES / 16; i += CTA_T) reinterpret_cast<uint4*>(c.sm + SM_A)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
-  c.tmem = c.tmem_base + 128u * c.grp;
+  c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 64);
+  c.tmem = c.tmem_base + 256u * c.grp;
   c.wbar = wbar;      // waited on in forward(): the weight load overlaps the first tile's map lookups and input staging
 }
 
+// End of the tile loop: every group has consumed its last accumulator, every weight copy has landed (a CTA without
+// tiles never waited for them) -- from here on the weight images are free to be reused as reduction scratch.
 __device__ __forceinline__ void epilogue_free(Ctx& c) {
+  for (int l = 0; l < NWBAR; ++l) mbar_wait(c.wbar + 8 * l, 0);
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
@@ -538,7 +586,7 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
   sdf_tiles(c, M, P, obs, n, indexer, latents, obs_count, robust, robust_k, with_J, acc);
   epilogue_free(c);
   PROF_MARK(c);
-  block_reduce_parts(acc, c.part, packed, reinterpret_cast<double*>(c.sm + SM_A));
+  block_reduce_parts(acc, c.part, packed, reinterpret_cast<double*>(c.sm));
   PROF_MARK(c);                                  // kernel end
 }
 
@@ -579,7 +627,7 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
 #pragma unroll
     for (int i = 0; i < 3; ++i) R.P.kt[i] = gs->kt[i];
     const int tg = threadIdx.x % GT, npx = R.H * R.W;
-    volatile int* slotp = reinterpret_cast<volatile int*>(c.sm + SM_BAR + 32 + 4 * c.grp);
+    volatile int* slotp = reinterpret_cast<volatile int*>(c.sm + SM_BAR + 72 + 4 * c.grp);
     for (;;) {
       if (tg == 0) *slotp = atomicAdd(&gs->rgb_cursor, 1);
       group_sync(c.grp);
@@ -604,16 +652,16 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
     }
   }
   PROF_MARK(c);                                  // pixels done
-  epilogue_free(c);                              // block-wide barrier; the tile buffers are scratch from here on
+  epilogue_free(c);                              // block-wide barrier; the weight images are scratch from here on
   PROF_MARK(c);                                  // all groups done
-  // Block sums through shared memory (the tile buffers are idle): every thread writes its partial sums column-wise, then 8
+  // Block sums through shared memory (the weight images are idle): every thread writes its partial sums column-wise, then 8
   // threads per value add their share in float64 and meet with three shuffles.  (A shuffle-only reduction of 45 doubles
   // per thread is bound by the SM's one-warp-per-clock shuffle unit: measured 6.5 us here.)
   {
     constexpr int NS = HG_PER_THREAD * NPART;                     // 32 SDF rows (29 used); a row holds the GROUPS * T threads of one part
     constexpr int LDS_ = GROUPS * T + 8, LDR = CTA_T + 8;         // padded rows: the 4 values a warp reads land in distinct banks
-    static_assert((NS * LDS_ + 29 * LDR) * 4 + gn::STEP_SCRATCH_BYTES <= GROUPS * SM_TILE_BYTES, "reduction scratch exceeds the tile buffers");
-    float* bs = reinterpret_cast<float*>(c.sm + SM_A);
+    static_assert((NS * LDS_ + 29 * LDR) * 4 + gn::STEP_SCRATCH_BYTES <= IMG_END, "reduction scratch exceeds the (now idle) weight images");
+    float* bs = reinterpret_cast<float*>(c.sm);
     float* br = bs + NS * LDS_;
 #pragma unroll
     for (int k = 0; k < HG_PER_THREAD; ++k) bs[(c.part * HG_PER_THREAD + k) * LDS_ + c.grp * T + c.row] = acc[k];
@@ -646,7 +694,7 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
   __threadfence();
   __syncthreads();
   PROF_MARK(c);                                  // sums out
-  gn::tail_step(gs, sa, c.sm + GROUPS * SM_TILE_BYTES + SM_A - gn::STEP_SCRATCH_BYTES, reinterpret_cast<int*>(c.sm + SM_BAR + 56));
+  gn::tail_step(gs, sa, c.sm + IMG_END - gn::STEP_SCRATCH_BYTES, reinterpret_cast<int*>(c.sm + SM_BAR + 80));
   PROF_MARK(c);                                  // kernel end (block 0; the step runs in whichever block finishes last)
 }
 

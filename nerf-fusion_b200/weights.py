@@ -86,15 +86,18 @@ def _swizzled_image(mat):
 
 
 def pack_decoder_tc(M, small):
-    """FP16 images for the tcgen05 engine + the FP32 small block, as bytes (uint8).  One image per layer serves the
-    forward pass (read K-major) and the reverse pass (read MN-major).  Input columns are duplicated (hi | lo halves)."""
+    """FP16 images for the tcgen05 engine + the FP32 small block, as bytes (uint8); layout csrc/decoder_tc.cu IMG_*.
+    Every matrix is split hi = fp16(W), lo = fp16(W - hi) (the engine computes A_hi W_hi + A_lo W_hi + A_hi W_lo);
+    one image per layer and half serves the forward pass (read K-major) and the reverse pass (read MN-major)."""
     W0, W1, W2, W3 = M["W0"], M["W1"], M["W2"], M["W3"]
-    w0 = np.concatenate([W0, W0], axis=1)                                   # (128, 64)
-    w3a = np.zeros((128, 128), np.float32); w3a[:, :96] = W3[:, :96]
-    w3b = np.concatenate([W3[:, 96:128], W3[:, 96:128]], axis=1)            # (128, 64)
-    imgs = [_swizzled_image(w0), _swizzled_image(W1), _swizzled_image(W2), _swizzled_image(w3a), _swizzled_image(w3b)]
+
+    def hi(m):
+        return m.astype(np.float16).astype(np.float32)
+    w0 = np.concatenate([hi(W0), W0 - hi(W0)], axis=1)                      # (128, 64): hi | lo
+    imgs = [_swizzled_image(w0), _swizzled_image(hi(W1)), _swizzled_image(W1 - hi(W1)), _swizzled_image(hi(W2)),
+            _swizzled_image(W2 - hi(W2)), _swizzled_image(hi(W3)), _swizzled_image(W3 - hi(W3))]
     img = np.concatenate(imgs).view(np.uint8)
-    assert img.size == 122880, img.size
+    assert img.size == 196608, img.size
     sm = np.zeros(6144 // 4, np.float32); sm[:small.size] = small
     return np.concatenate([img, sm.view(np.uint8)])
 

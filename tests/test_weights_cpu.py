@@ -70,7 +70,7 @@ def test_tc_images_follow_the_kernel_swizzle(dfb, weights):
     """FP16 SWIZZLE_128B images of the tcgen05 engine: element (row, k) of a layer lives at
     block (k // 64), row, 16-byte chunk ((k % 64) // 8) ^ (row & 7), lane k % 8 (csrc/decoder_tc.cu)."""
     blob = dfb.weights.pack_decoder(weights)
-    assert blob.size == 91624 + 32256
+    assert blob.size == 91624 + 50688
     tc = blob[91624:].view(np.uint8)
     M = dfb.weights.decoder_matrices(weights)
 
@@ -81,13 +81,19 @@ def test_tc_images_follow_the_kernel_swizzle(dfb, weights):
             for c in range(K // 8):
                 out[r, 8 * c: 8 * c + 8] = h[c // 8, r, (c % 8) ^ (r & 7)]
         return out
-    w0 = read(0, 128, 64)
-    assert np.array_equal(w0[:, :32], M["W0"].astype(np.float16)) and np.array_equal(w0[:, 32:], M["W0"].astype(np.float16))
-    assert np.array_equal(read(16384, 128, 128), M["W1"].astype(np.float16))
-    assert np.array_equal(read(49152, 96, 128), M["W2"].astype(np.float16))
-    w3a = read(73728, 128, 128)
-    assert np.array_equal(w3a[:, :96], M["W3"][:, :96].astype(np.float16)) and not w3a[:, 96:].any()
-    w3b = read(106496, 128, 64)
-    assert np.array_equal(w3b[:, :32], M["W3"][:, 96:].astype(np.float16)) and np.array_equal(w3b[:, 32:], w3b[:, :32])
-    small = tc[122880:].view(np.float32)
+    def hi(m):
+        return m.astype(np.float16)
+
+    def lo(m):
+        return (m - m.astype(np.float16).astype(np.float32)).astype(np.float16)
+    w0 = read(0, 128, 64)                                    # hi | lo halves of W0 (csrc/decoder_tc.cu IMG_*)
+    assert np.array_equal(w0[:, :32], hi(M["W0"])) and np.array_equal(w0[:, 32:], lo(M["W0"]))
+    assert np.array_equal(read(16384, 128, 128), hi(M["W1"])) and np.array_equal(read(49152, 128, 128), lo(M["W1"]))
+    assert np.array_equal(read(81920, 96, 128), hi(M["W2"])) and np.array_equal(read(106496, 96, 128), lo(M["W2"]))
+    assert np.array_equal(read(131072, 128, 128), hi(M["W3"])) and np.array_equal(read(163840, 128, 128), lo(M["W3"]))
+    # hi + lo carries ~22 significant bits of every weight
+    for k, off, rows in (("W1", (16384, 49152), 128), ("W3", (131072, 163840), 128)):
+        rec = read(off[0], rows, 128).astype(np.float32) + read(off[1], rows, 128).astype(np.float32)
+        assert np.abs(rec - M[k]).max() <= 2.0 ** -21 * np.abs(M[k]).max()
+    small = tc[196608:].view(np.float32)
     assert np.array_equal(small[:1512], blob[90112:90112 + 1512])

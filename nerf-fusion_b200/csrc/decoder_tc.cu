@@ -131,13 +131,17 @@ __device__ int g_prof_n;
 // Tile schedule of a persistent CTA: full rounds give every (CTA, group) slot one tile; the last, partial round hands its
 // tiles out one per CTA first (group 0 of every CTA, then group 1), so that a CTA whose sibling group has nothing left
 // runs its tile with the SM's issue slots and the tensor pipe to itself.  Returns -1 when the group is done.
-__device__ __forceinline__ long long tile_of(const Ctx& c, long long n, long long rnd) {
-  const long long tiles = (n + T - 1) / T, slots = (long long)gridDim.x * GROUPS;
-  const long long full = tiles / slots;
-  if (rnd < full) return rnd * slots + (long long)blockIdx.x * GROUPS + c.grp;
-  if (rnd > full) return -1;
-  const long long j = (long long)c.grp * gridDim.x + blockIdx.x;
-  return j < tiles - full * slots ? full * slots + j : -1;
+struct Sched { int tiles, slots, full; };
+__device__ __forceinline__ Sched make_sched(long long n) {
+  Sched s;
+  s.tiles = (int)((n + T - 1) / T); s.slots = (int)gridDim.x * GROUPS; s.full = s.tiles / s.slots;
+  return s;
+}
+__device__ __forceinline__ int tile_of(const Ctx& c, const Sched& s, int rnd) {
+  if (rnd < s.full) return rnd * s.slots + (int)blockIdx.x * GROUPS + c.grp;
+  if (rnd > s.full) return -1;
+  const int j = c.grp * (int)gridDim.x + (int)blockIdx.x;
+  return j < s.tiles - s.full * s.slots ? s.full * s.slots + j : -1;
 }
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
@@ -166,17 +170,17 @@ __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0,
 // this thread's TMEM lane: lanes 32 (warp % 4) .. + 31 are the only ones a warp may touch
 __device__ __forceinline__ uint32_t lane_base(const Ctx& c) { return c.tmem + ((uint32_t)(c.row & ~31) << 16); }
 
-// 32 consecutive values of this thread's row -> hi / lo FP16 pairs -> the A operand at K index k0 .. k0 + 31
-__device__ __forceinline__ void store_a32(const Ctx& c, int k0, const float* h) {
+// 16 consecutive values of this thread's row -> hi / lo FP16 pairs -> the A operand at K index k0 .. k0 + 15
+// (epilogues work in 16-column pieces: 16 accumulator + 16 packed registers in flight keep the kernels spill-free)
+constexpr int EW = 16;               // epilogue piece width (columns)
+constexpr int NPIECE = CW / EW;      // pieces per thread per layer
+__device__ __forceinline__ void store_a16(const Ctx& c, int k0, const float* h) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) split_h2(h[2 * q], h[2 * q + 1], hi[q], lo[q]);
   const uint32_t tb = lane_base(c) + (uint32_t)(k0 >> 1);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) split_h2(h[16 * half + 2 * q], h[16 * half + 2 * q + 1], hi[q], lo[q]);
-    tmem_st8(tb + TM_AH + 8 * half, hi);
-    tmem_st8(tb + TM_AL + 8 * half, lo);
-  }
+  tmem_st8(tb + TM_AH, hi);
+  tmem_st8(tb + TM_AL, lo);
 }
 
 // the network inputs of this thread's half (16 of 32), kept packed in registers, -> K 96 + 16 part .. of the A operand
@@ -192,22 +196,22 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const uint32_t tb = lane_base(c) + TM_D;
 #pragma unroll
-  for (int jj = 0; jj < CW / 32; ++jj) {
-    const int cb = CW * c.part + 32 * jj;
+  for (int q = 0; q < NPIECE; ++q) {
+    const int cb = CW * c.part + EW * q;
     if (cb < NCOLS) {                       // warp-uniform
-      float v[32];
-      tmem_ld32(tb + cb, v);
+      float v[EW];
+      tmem_ld16(tb + cb, v);
       uint32_t m = 0;
       const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + cb);
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
+      for (int i4 = 0; i4 < EW / 4; ++i4) {
         const float4 b = b4[i4];
         const float a0 = v[4 * i4] + b.x, a1 = v[4 * i4 + 1] + b.y, a2 = v[4 * i4 + 2] + b.z, a3 = v[4 * i4 + 3] + b.w;
         m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
         v[4 * i4] = fmaxf(a0, 0.f); v[4 * i4 + 1] = fmaxf(a1, 0.f); v[4 * i4 + 2] = fmaxf(a2, 0.f); v[4 * i4 + 3] = fmaxf(a3, 0.f);
       }
-      c.mask[layer][jj] = m;
-      store_a32(c, cb, v);
+      if (q & 1) c.mask[layer][q >> 1] |= m << 16; else c.mask[layer][q >> 1] = m;
+      store_a16(c, cb, v);
     }
   }
 }
@@ -217,15 +221,15 @@ template <int NCOLS>
 __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
   const uint32_t tb = lane_base(c) + TM_D;
 #pragma unroll
-  for (int jj = 0; jj < CW / 32; ++jj) {
-    const int cb = CW * c.part + 32 * jj;
+  for (int q = 0; q < NPIECE; ++q) {
+    const int cb = CW * c.part + EW * q;
     if (cb < NCOLS) {
-      float v[32];
-      tmem_ld32(tb + cb, v);
-      const uint32_t m = c.mask[layer][jj];
+      float v[EW];
+      tmem_ld16(tb + cb, v);
+      const uint32_t m = c.mask[layer][q >> 1] >> (16 * (q & 1));
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
-      store_a32(c, cb, v);
+      for (int i = 0; i < EW; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+      store_a16(c, cb, v);
     }
   }
 }
@@ -281,20 +285,19 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   TC_LAYER((issue3<8, 128, false, 128>(c, 0, IMG_W3H, IMG_W3L)));
   // heads in FP32 straight from the accumulator (h3 never leaves TMEM/registers); each thread sums its 64 columns
   const uint32_t tb = lane_base(c) + TM_D;
-  const int col0 = CW * c.part;
   float zu[2] = {0.f, 0.f};
   float z1 = 0.f, u1 = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < CW / 32; ++jj) {
-    const int cb = col0 + 32 * jj;
-    float v[32];
-    tmem_ld32(tb + cb, v);
+  for (int q = 0; q < NPIECE; ++q) {
+    const int cb = CW * c.part + EW * q;
+    float v[EW];
+    tmem_ld16(tb + cb, v);
     uint32_t m = 0;
     const float4* b4 = reinterpret_cast<const float4*>(sm + DS_B3 + cb);
     const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + cb);
     const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + cb);
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
+    for (int i4 = 0; i4 < EW / 4; ++i4) {
       const float4 b = b4[i4], wz = w4[i4], wv = wu[i4];
       const float a0 = v[4 * i4] + b.x, a1 = v[4 * i4 + 1] + b.y, a2 = v[4 * i4 + 2] + b.z, a3 = v[4 * i4 + 3] + b.w;
       m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
@@ -302,7 +305,7 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
       zu[0] = fmaf(wz.x, h0, zu[0]); z1 = fmaf(wz.y, h1, z1); zu[0] = fmaf(wz.z, h2, zu[0]); z1 = fmaf(wz.w, h3, z1);
       zu[1] = fmaf(wv.x, h0, zu[1]); u1 = fmaf(wv.y, h1, u1); zu[1] = fmaf(wv.z, h2, zu[1]); u1 = fmaf(wv.w, h3, u1);
     }
-    c.mask[3][jj] = m;
+    if (q & 1) c.mask[3][q >> 1] |= m << 16; else c.mask[3][q >> 1] = m;
   }
   zu[0] += z1; zu[1] += u1;
   exchange(c, zu, 2);
@@ -315,59 +318,60 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
 template <bool HAS_U = true>
 __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, float g[3]) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  const int col0 = CW * c.part;
+  const uint32_t tb = lane_base(c) + TM_D;
   float ga[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int jj = 0; jj < CW / 32; ++jj) {
-    const int cb = col0 + 32 * jj;
-    float d[32];
-    const uint32_t m = c.mask[3][jj];
+  for (int q = 0; q < NPIECE; ++q) {                                 // delta3 = (seed_z w4 + seed_u wu) * [a3 > 0]
+    const int cb = CW * c.part + EW * q;
+    float d[EW];
+    const uint32_t m = c.mask[3][q >> 1] >> (16 * (q & 1));
     const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + cb);
     const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + cb);
-    const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W3X + 3 * cb);
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
+    for (int i4 = 0; i4 < EW / 4; ++i4) {
       const float4 wz = w4[i4];
       const float4 wv = HAS_U ? wu[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 ta = t4[3 * i4], tb = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];     // taps of 4 consecutive units, 3 floats each
       const uint32_t mm = m >> (4 * i4);
-      const float d0 = (mm & 1u) ? (HAS_U ? fmaf(seed_z, wz.x, seed_u * wv.x) : seed_z * wz.x) : 0.f;
-      const float d1 = (mm & 2u) ? (HAS_U ? fmaf(seed_z, wz.y, seed_u * wv.y) : seed_z * wz.y) : 0.f;
-      const float d2 = (mm & 4u) ? (HAS_U ? fmaf(seed_z, wz.z, seed_u * wv.z) : seed_z * wz.z) : 0.f;
-      const float d3 = (mm & 8u) ? (HAS_U ? fmaf(seed_z, wz.w, seed_u * wv.w) : seed_z * wz.w) : 0.f;
-      d[4 * i4] = d0; d[4 * i4 + 1] = d1; d[4 * i4 + 2] = d2; d[4 * i4 + 3] = d3;
-      ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
-      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb.x, d1, ga[1]); ga[2] = fmaf(tb.y, d1, ga[2]);
-      ga[0] = fmaf(tb.z, d2, ga[0]); ga[1] = fmaf(tb.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
-      ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
+      d[4 * i4] = (mm & 1u) ? (HAS_U ? fmaf(seed_z, wz.x, seed_u * wv.x) : seed_z * wz.x) : 0.f;
+      d[4 * i4 + 1] = (mm & 2u) ? (HAS_U ? fmaf(seed_z, wz.y, seed_u * wv.y) : seed_z * wz.y) : 0.f;
+      d[4 * i4 + 2] = (mm & 4u) ? (HAS_U ? fmaf(seed_z, wz.z, seed_u * wv.z) : seed_z * wz.z) : 0.f;
+      d[4 * i4 + 3] = (mm & 8u) ? (HAS_U ? fmaf(seed_z, wz.w, seed_u * wv.w) : seed_z * wz.w) : 0.f;
     }
-    store_a32(c, cb, d);
+    store_a16(c, cb, d);
   }
-  TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W3H, IMG_W3L)));   // D[:, :96] = delta2 = delta3 * W3[:, :96]  (cols 96.. = d/d(input) via the skip, unused here)
+  // D[:, :96] = delta2 = delta3 * W3[:, :96]; D[:, 96:128] = delta3 * W3[:, 96:128] = d/d(input) through the skip connection:
+  // its last three columns are the xyz part, so the tensor core also delivers the layer-3 taps
+  TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W3H, IMG_W3L)));
+  if (c.part == NPART - 1) {
+    float t[4];
+    tmem_ld4(tb + 124, t);
+    ga[0] = t[1]; ga[1] = t[2]; ga[2] = t[3];
+  }
   epi_bwd<96>(c, 2);
   TC_LAYER((issue3<6, 128, true, 96>(c, 0, IMG_W2H, IMG_W2L)));    // delta1 = delta2 * W2
   epi_bwd<128>(c, 1);
   TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W1H, IMG_W1L)));   // delta0 = delta1 * W1 (masked below)
-  const uint32_t tb = lane_base(c) + TM_D;
+  float gb[3] = {0.f, 0.f, 0.f};                                   // second set of accumulators: two dependent FMA chains per output
 #pragma unroll
-  for (int jj = 0; jj < CW / 32; ++jj) {
-    const int cb = col0 + 32 * jj;
-    float v[32];
-    tmem_ld32(tb + cb, v);
-    const uint32_t m = c.mask[0][jj];
+  for (int q = 0; q < NPIECE; ++q) {
+    const int cb = CW * c.part + EW * q;
+    float v[EW];
+    tmem_ld16(tb + cb, v);
+    const uint32_t m = c.mask[0][q >> 1] >> (16 * (q & 1));
     const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * cb);
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 ta = t4[3 * i4], tb_ = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];
+    for (int i4 = 0; i4 < EW / 4; ++i4) {
+      const float4 ta = t4[3 * i4], tb_ = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];     // taps of 4 consecutive units, 3 floats each
       const uint32_t mm = m >> (4 * i4);
       const float d0 = (mm & 1u) ? v[4 * i4] : 0.f, d1 = (mm & 2u) ? v[4 * i4 + 1] : 0.f;
       const float d2 = (mm & 4u) ? v[4 * i4 + 2] : 0.f, d3 = (mm & 8u) ? v[4 * i4 + 3] : 0.f;
       ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
-      ga[0] = fmaf(ta.w, d1, ga[0]); ga[1] = fmaf(tb_.x, d1, ga[1]); ga[2] = fmaf(tb_.y, d1, ga[2]);
+      gb[0] = fmaf(ta.w, d1, gb[0]); gb[1] = fmaf(tb_.x, d1, gb[1]); gb[2] = fmaf(tb_.y, d1, gb[2]);
       ga[0] = fmaf(tb_.z, d2, ga[0]); ga[1] = fmaf(tb_.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);
-      ga[0] = fmaf(tc_.y, d3, ga[0]); ga[1] = fmaf(tc_.z, d3, ga[1]); ga[2] = fmaf(tc_.w, d3, ga[2]);
+      gb[0] = fmaf(tc_.y, d3, gb[0]); gb[1] = fmaf(tc_.z, d3, gb[1]); gb[2] = fmaf(tc_.w, d3, gb[2]);
     }
   }
+  ga[0] += gb[0]; ga[1] += gb[1]; ga[2] += gb[2];
   exchange(c, ga, 3);
   g[0] = ga[0]; g[1] = ga[1]; g[2] = ga[2];
 }
@@ -476,8 +480,9 @@ __global__ void __launch_bounds__(CTA_T, 1) explicit_kernel(const float* __restr
                                                         float* __restrict__ sdf, float* __restrict__ std_) {
   Ctx c;
   prologue(c, blob);
-  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
-    const int i = (int)(tile * T) + c.row;
+  const Sched S = make_sched(n);
+  for (int rnd = 0, tile; (tile = tile_of(c, S, rnd)) >= 0; ++rnd) {
+    const int i = tile * T + c.row;
     {
       const float* xr = x + (size_t)(i < n ? i : 0) * 32;
       const float rel3[3] = {i < n ? xr[29] : 0.f, i < n ? xr[30] : 0.f, i < n ? xr[31] : 0.f};
@@ -497,8 +502,9 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
                                                        const float* __restrict__ g_std, float* __restrict__ grad_xyz) {
   Ctx c;
   prologue(c, blob);
-  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
-    const int i = (int)(tile * T) + c.row;
+  const Sched S = make_sched(n);
+  for (int rnd = 0, tile; (tile = tile_of(c, S, rnd)) >= 0; ++rnd) {
+    const int i = tile * T + c.row;
     bool valid = false;
     long long slot = 0;
     float rel[3] = {0.f, 0.f, 0.f};
@@ -534,8 +540,9 @@ __global__ void __launch_bounds__(CTA_T, 1) get_sdf_kernel(MapDev M, const float
 __device__ __forceinline__ void sdf_tiles(Ctx& c, const MapDev& M, const PoseDev& P, const float* __restrict__ obs, int n,
                                           const int64_t* __restrict__ indexer, const float* __restrict__ latents,
                                           const float* __restrict__ obs_count, int robust, float robust_k, int with_J, float* acc) {
-  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
-    const int i = (int)(tile * T) + c.row;
+  const Sched S = make_sched(n);
+  for (int rnd = 0, tile; (tile = tile_of(c, S, rnd)) >= 0; ++rnd) {
+    const int i = tile * T + c.row;
     PROF_MARK(c);                                // tile start
     bool valid = false;
     long long slot = 0;
@@ -704,8 +711,9 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_low_kernel(const float* __restr
   Ctx c;
   prologue(c, blob);
   const long long r3 = (long long)r * r * r, n = (long long)B * r3;
-  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
-    const long long i = tile * T + c.row;
+  const Sched S = make_sched(n);
+  for (int rnd = 0, tile; (tile = tile_of(c, S, rnd)) >= 0; ++rnd) {
+    const long long i = (long long)tile * T + c.row;
     const bool valid = i < n;
     float rel[3] = {0.f, 0.f, 0.f};
     long long slot = 0;
@@ -731,8 +739,9 @@ __global__ void __launch_bounds__(CTA_T, 1) cube_refine_kernel(const float* __re
   const int R = 2 * r;
   const long long R3 = (long long)R * R * R;
   const int n = *refine_count;
-  for (long long rnd = 0, tile; (tile = tile_of(c, n, rnd)) >= 0; ++rnd) {
-    const int t = (int)(tile * T) + c.row;
+  const Sched S = make_sched(n);
+  for (int rnd = 0, tile; (tile = tile_of(c, S, rnd)) >= 0; ++rnd) {
+    const int t = tile * T + c.row;
     const bool valid = t < n;
     float rel[3] = {0.f, 0.f, 0.f};
     long long slot = 0, i = 0;

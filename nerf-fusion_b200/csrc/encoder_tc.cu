@@ -1,15 +1,19 @@
 // tcgen05 encoder engine (sm_100a): the per-sample encoder MLP 6 -> 32 -> 64 -> 256 -> 29 (network/di_encoder.py:26-30,
 // BatchNorm folded on the host) on the tensor cores, fused with the scatter-add into the per-voxel accumulators
-// (map.py:446-449, indexing.cu:59-71).  Same structure as decoder_tc.cu: FP16 weight images resident in shared memory
-// (one bulk-TMA load per CTA), FP32 accumulators in TMEM (256 columns per tile), 8 warps per tile running the
-// bias/ReLU/FP16 epilogues.  Precision: every weight matrix is stored as TWO FP16 images, hi = fp16(W) and
-// lo = fp16(W - hi), and each layer accumulates A*hi + A*lo in the same TMEM accumulator (weights effectively ~22 bits).
-// The inputs of layers 0, 1 and 2 are split hi + lo as well: the activation tile holds [hi | lo] side by side and the
-// hi weight image is duplicated under both halves (the lo image only under the hi half; lo x lo is below FP32 noise).
-// Layer 1's 32 inputs carry most of the FP16 sensitivity (1.2e-3 of the output range when rounded), layer 2's 64 inputs
-// 3.6e-4; only the 256 inputs of the output layer stay single FP16 (4.8e-4 worst case per sample on random inputs, far
-// less after the per-voxel mean), so the latents stay inside the 1e-3 parity tolerance.  The weight images (152 KB)
-// leave room for one tile in flight per CTA.
+// (map.py:446-449, indexing.cu:59-71).
+//
+// Same construction as decoder_tc.cu: FP16 weight images resident in shared memory (bulk-TMA loads), ACTIVATIONS RESIDENT
+// IN TENSOR MEMORY (every layer is D[tmem] = A[tmem] * B[smem], the epilogue warps turn the FP32 accumulator into the
+// next layer's A operand with tcgen05.ld / tcgen05.st), and every product computed as three FP16 MMAs
+//     A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo      (hi = fp16(x), lo = fp16(x - hi))
+// so the latents agree with an FP32 evaluation to ~1e-6 instead of the 2e-4 of single-FP16 operands.
+//
+// Tensor-memory plan (224 of 256 columns, so TWO CTAs -- two tiles -- are resident per SM; the images take 110 KB):
+//   X = [  0,128)  accumulator of layers 0, 1 and of one 128-column HALF of layer 2; the layer-2 epilogue writes the
+//                  layer-3 operand IN PLACE: a thread reads 16 FP32 columns and stores 8 hi + 8 lo packed columns over them
+//   Y = [128,192)  A operand of layers 0, 1, 2 (per 16-element K step: 8 hi columns, then 8 lo columns)
+//   Z = [192,224)  layer-3 accumulator (the 29 latents), accumulated over the two K halves
+// Layer order per tile: L0, L1, L2a, L3a, L2b, L3b.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -18,31 +22,29 @@ namespace dfb {
 namespace etc {
 using namespace tcp;
 
-constexpr int GROUPS = 1;
-constexpr int NPART = 2;
-constexpr int GT = T * NPART;
-constexpr int CTA_T = GT * GROUPS;
-// ---- blob (bytes) -----------------------------------------------------------------------------------------------------
-constexpr int IMG_W0 = 0;          // [ 32 rows x 64]: cols 0..5 = W0' (x hi inputs), cols 8..13 = W0' (x lo inputs)
-constexpr int IMG_W1 = 4096;       // [ 64 rows x 64]: cols 0..31 = W1' (x hi), cols 32..63 = W1' (x lo)
-constexpr int IMG_W2 = 12288;      // 2 blocks x [256 rows x 64]: block 0 = W2' (x hi), block 1 = W2' (x lo)
-constexpr int IMG_W3 = 77824;      // 4 blocks x [32 rows x 64]: rows 0..28 = W3
-constexpr int IMG_W0L = 94208;     // lo images: [32 x 64] cols 0..5
-constexpr int IMG_W1L = 98304;     //            [64 x 64] cols 0..31
-constexpr int IMG_W2L = 106496;    //            [256 x 64]
-constexpr int IMG_W3L = 139264;    //            4 blocks x [32 x 64]
-constexpr int IMG_END = 155648;
+constexpr int NPART = 2;           // threads per row
+constexpr int CTA_T = T * NPART;   // one tile per CTA, two CTAs per SM
+// ---- blob (bytes): FP16 SWIZZLE_128B K-major images; packed by weights.pack_encoder_tc -----------------------------
+constexpr int IMG_W0 = 0;          // [ 32 rows x 64]: cols 0..5 = hi(W0), cols 16..21 = lo(W0)
+constexpr int IMG_W1 = 4096;       // [ 64 rows x 64]: cols 0..31 = hi(W1), cols 32..63 = lo(W1)
+constexpr int IMG_W2H = 12288;     // [256 rows x 64]
+constexpr int IMG_W2L = 45056;
+constexpr int IMG_W3H = 77824;     // 4 blocks x [32 rows x 64]: rows 0..28 = W3
+constexpr int IMG_W3L = 94208;
+constexpr int IMG_END = 110592;
 constexpr int ES_B0 = 0, ES_B1 = 32, ES_B2 = 96, ES_B3 = 352;   // FP32 biases (floats)
 constexpr int SMALL_BYTES = 2048;
-constexpr int BLOB_BYTES = IMG_END + SMALL_BYTES;   // 157696 = 154 * 1024
-// ---- shared memory ------------------------------------------------------------------------------------------------------
+constexpr int BLOB_BYTES = IMG_END + SMALL_BYTES;
+static_assert(BLOB_BYTES == 112640, "integrate.cu ENC_TC_BLOB_BYTES / weights.pack_encoder_tc");
+// ---- shared memory -------------------------------------------------------------------------------------------------
 constexpr int SM_SMALL = IMG_END;
-constexpr int SM_A = BLOB_BYTES;                    // activation tile, 4 blocks x [128 x 64] fp16 per group
-constexpr int SM_TILE_BYTES = 65536;
-constexpr int SM_BAR = SM_A + GROUPS * SM_TILE_BYTES;
+constexpr int SM_BAR = BLOB_BYTES;
 constexpr int SM_TOTAL = SM_BAR + 64;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;
-constexpr int TMEM_COLS = 256 * GROUPS;
+static_assert(2 * (SM_ALLOC + 1024) <= 233472, "two CTAs per SM");
+// ---- tensor memory -------------------------------------------------------------------------------------------------
+constexpr int TM_X = 0, TM_Y = 128, TM_Z = 192;
+constexpr int TMEM_COLS = 256;
 
 struct Sample {   // same 32-byte record as integrate.cu
   int slot;
@@ -53,32 +55,49 @@ struct Sample {   // same 32-byte record as integrate.cu
 
 struct Ctx {
   uint8_t* sm;
-  uint32_t sa, tmem, tmem_base, mma_bar, wbar, phase;
-  int row, part, grp;
-  uint32_t a_off;
+  uint32_t sa, tmem, mma_bar, wbar, phase;
+  int row, part;
 };
 
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); }
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
-template <int KSTEPS, int N, int B_ROWS>
-__device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_addr, bool accumulate_first = false) {
+// Issuing thread only.  A: KSTEPS K steps from tensor memory at a_tmem, 16 columns apart (8 hi columns, then 8 lo); A_LO picks
+// the lo half.  B: K-major image at b_addr, B_ROWS rows per 64-column block, rows [N0, N0 + N), starting at K step B_S0.
+template <int KSTEPS, int N, int B_ROWS, int B_S0, bool A_LO, int N0 = 0>
+__device__ __forceinline__ void issue(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool accumulate_first) {
   constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
-  const uint64_t ad0 = smem_desc(a_addr, 16, 1024);
-  const uint64_t bd0 = smem_desc(b_addr, 16, 1024);
+  const uint64_t bd0 = smem_desc(b_addr + N0 * 128, 16, 1024);
 #pragma unroll
   for (int s = 0; s < KSTEPS; ++s) {
-    const uint64_t ad = ad0 + (uint64_t)(((s >> 2) * 16384 + (s & 3) * 32) >> 4);
-    const uint64_t bd = bd0 + (uint64_t)(((s >> 2) * (B_ROWS * 128) + (s & 3) * 32) >> 4);
-    mma_f16(c.tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    const int sb = s + B_S0;
+    const uint64_t bd = bd0 + (uint64_t)(((sb >> 2) * (B_ROWS * 128) + (sb & 3) * 32) >> 4);
+    mma_f16_ts(d_tmem, a_tmem + 16u * s + (A_LO ? 8u : 0u), bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
   }
+}
+// A_hi W_hi + A_lo W_hi + A_hi W_lo with the hi / lo weight images side by side in one 64-column block (lo at K step LO_S0)
+template <int KSTEPS, int N, int B_ROWS, int LO_S0>
+__device__ __forceinline__ void issue3_packed(uint32_t d, uint32_t a, uint32_t img) {
+  issue<KSTEPS, N, B_ROWS, 0, false>(d, a, img, false);
+  issue<KSTEPS, N, B_ROWS, 0, true>(d, a, img, true);
+  issue<KSTEPS, N, B_ROWS, LO_S0, false>(d, a, img, true);
+}
+// same with separate hi / lo images, rows [N0, N0 + N) of both, K steps from B_S0
+template <int KSTEPS, int N, int B_ROWS, int B_S0, int N0>
+__device__ __forceinline__ void issue3(uint32_t d, uint32_t a, uint32_t img_hi, uint32_t img_lo, bool accumulate_first) {
+  issue<KSTEPS, N, B_ROWS, B_S0, false, N0>(d, a, img_hi, accumulate_first);
+  issue<KSTEPS, N, B_ROWS, B_S0, true, N0>(d, a, img_hi, true);
+  issue<KSTEPS, N, B_ROWS, B_S0, false, N0>(d, a, img_lo, true);
 }
 
 #define ETC_LAYER(ISSUE_STMT)                         \
   do {                                                \
-    fence_proxy_async();                              \
+    tmem_st_wait();                                   \
     tc_fence_before();                                \
-    group_sync(c.grp);                                \
-    if (c.row == 0 && c.part == 0) {                  \
+    __syncthreads();                                  \
+    if (threadIdx.x == 0) {                           \
       tc_fence_after();                               \
       ISSUE_STMT;                                     \
       mma_commit(c.mma_bar);                          \
@@ -88,52 +107,37 @@ __device__ __forceinline__ void issue(const Ctx& c, uint32_t a_addr, uint32_t b_
     tc_fence_after();                                 \
   } while (0)
 
-// hidden-layer epilogue: this thread's NCOLS / NPART columns: relu(D + b) -> FP16 activation tile; with SPLIT the
-// FP16 residual of every activation goes NCOLS columns further right ([hi | lo] layout)
-template <int NCOLS, bool SPLIT>
-__device__ __forceinline__ void epi_hidden(Ctx& c, int bias_off) {
+__device__ __forceinline__ uint32_t lane_base(const Ctx& c) { return c.tmem + ((uint32_t)(c.row & ~31) << 16); }
+
+// 16 values of this thread's row -> 8 hi + 8 lo packed columns at dst .. dst + 15
+__device__ __forceinline__ void store_step(const Ctx& c, uint32_t dst_col, const float* h) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) split_h2(h[2 * q], h[2 * q + 1], hi[q], lo[q]);
+  const uint32_t tb = lane_base(c) + dst_col;
+  tmem_st8(tb, hi);
+  tmem_st8(tb + 8, lo);
+}
+
+// hidden-layer epilogue: relu(D + b) of NCOLS accumulator columns at X -> A operand K steps at dst (NCOLS / 16 steps);
+// this thread takes every NPART-th step.  In place when dst == TM_X (a step only overwrites the columns it was read from).
+template <int NCOLS>
+__device__ __forceinline__ void epi_hidden(Ctx& c, int bias_off, uint32_t dst) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  constexpr int CW = NCOLS / NPART;
-  const uint32_t tbase = c.tmem + ((uint32_t)(c.row & ~31) << 16);
-  const int colb = CW * c.part;
-  if constexpr (CW == 16) {
+  const uint32_t tb = lane_base(c) + TM_X;
+#pragma unroll
+  for (int q = 0; q < NCOLS / 16 / NPART; ++q) {
+    const int step = NPART * q + c.part;
     float v[16];
-    tmem_ld16(tbase + colb, v);
-    const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + colb);
+    tmem_ld16(tb + 16 * step, v);
+    const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + 16 * step);
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
       const float4 b = b4[i4];
       v[4 * i4] = fmaxf(v[4 * i4] + b.x, 0.f); v[4 * i4 + 1] = fmaxf(v[4 * i4 + 1] + b.y, 0.f);
       v[4 * i4 + 2] = fmaxf(v[4 * i4 + 2] + b.z, 0.f); v[4 * i4 + 3] = fmaxf(v[4 * i4 + 3] + b.w, 0.f);
     }
-    if constexpr (SPLIT) {
-      float lo[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
-      store_cols<16>(c.sm + c.a_off, 16384, c.row, NCOLS + colb, lo);
-    }
-    store_cols<16>(c.sm + c.a_off, 16384, c.row, colb, v);
-  } else {
-#pragma unroll
-    for (int jj = 0; jj < CW / 32; ++jj) {
-      const int col0 = colb + 32 * jj;
-      float v[32];
-      tmem_ld32(tbase + col0, v);
-      const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + col0);
-#pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
-        const float4 b = b4[i4];
-        v[4 * i4] = fmaxf(v[4 * i4] + b.x, 0.f); v[4 * i4 + 1] = fmaxf(v[4 * i4 + 1] + b.y, 0.f);
-        v[4 * i4 + 2] = fmaxf(v[4 * i4 + 2] + b.z, 0.f); v[4 * i4 + 3] = fmaxf(v[4 * i4 + 3] + b.w, 0.f);
-      }
-      if constexpr (SPLIT) {
-        float lo[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
-        store_cols<32>(c.sm + c.a_off, 16384, c.row, NCOLS + col0, lo);
-      }
-      store_cols<32>(c.sm + c.a_off, 16384, c.row, col0, v);
-    }
+    store_step(c, dst + 16 * step, v);
   }
 }
 
@@ -145,16 +149,14 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   c.sm = etc_smem_raw + pad;
   c.sa = raw + pad;
   c.phase = 0;
-  c.grp = threadIdx.x / GT;
-  c.part = (threadIdx.x % GT) / T;
+  c.part = threadIdx.x / T;
   c.row = threadIdx.x % T;
-  c.a_off = SM_A + c.grp * SM_TILE_BYTES;
   c.wbar = c.sa + SM_BAR;
   const uint32_t slot = c.sa + SM_BAR + 48;
-  c.mma_bar = c.sa + SM_BAR + 8 + 8 * c.grp;
+  c.mma_bar = c.sa + SM_BAR + 8;
   if (threadIdx.x == 0) {
     mbar_init(c.wbar, 1);
-    for (int g = 0; g < GROUPS; ++g) mbar_init(c.sa + SM_BAR + 8 + 8 * g, 1);
+    mbar_init(c.mma_bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -162,52 +164,49 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
   if (threadIdx.x == 0) {
     mbar_expect_tx(c.wbar, BLOB_BYTES);
     const char* src = reinterpret_cast<const char*>(blob);
-    for (int off = 0; off < BLOB_BYTES; off += 19712) bulk_g2s(c.sa + off, src + off, 19712u, c.wbar);   // 8 x 19712 B
+    for (int off = 0; off < BLOB_BYTES; off += 8192) bulk_g2s(c.sa + off, src + off, (uint32_t)min(8192, BLOB_BYTES - off), c.wbar);
   }
-  for (int i = threadIdx.x; i < GROUPS * SM_TILE_BYTES / 16; i += CTA_T) reinterpret_cast<uint4*>(c.sm + SM_A)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  c.tmem_base = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
-  c.tmem = c.tmem_base + 256u * c.grp;
+  c.tmem = *reinterpret_cast<volatile uint32_t*>(c.sm + SM_BAR + 48);
 }
 
-// one tile: in[6] of this row already known to both threads of the row.  Leaves the 29 outputs (+bias) of columns
-// [16 part, 16 part + 16) in out16.
+// one tile: in[6] of this row known to both threads of the row.  Leaves the outputs (+bias) of columns
+// [16 part, 16 part + 16) in out16 (29 are latents).
 __device__ __forceinline__ void encode_tile(Ctx& c, const float in[6], float out16[16]) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
-  {
-    float h[8];
+  if (c.part == 0) {                                              // layer-0 operand: one K step (6 inputs, 10 zeros)
+    float h[16];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const float hi = __half2float(__float2half_rn(in[k]));
-      h[k] = c.part == 0 ? hi : in[k] - hi;
-    }
-    h[6] = 0.f; h[7] = 0.f;
-    store_cols<8>(c.sm + c.a_off, 16384, c.row, 8 * c.part, h);     // cols 0..7 hi, 8..15 lo
+    for (int k = 0; k < 16; ++k) h[k] = k < 6 ? in[k] : 0.f;
+    store_step(c, TM_Y, h);
   }
-  mbar_wait(c.wbar, 0);
-  ETC_LAYER((issue<1, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W0)); (issue<1, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W0L, true)));
-  epi_hidden<32, true>(c, ES_B0);       // -> cols 0..31 hi, 32..63 lo
-  ETC_LAYER((issue<4, 64, 64>(c, c.sa + c.a_off, c.sa + IMG_W1)); (issue<2, 64, 64>(c, c.sa + c.a_off, c.sa + IMG_W1L, true)));
-  epi_hidden<64, true>(c, ES_B1);       // -> block 0 hi, block 1 lo
-  ETC_LAYER((issue<8, 256, 256>(c, c.sa + c.a_off, c.sa + IMG_W2)); (issue<4, 256, 256>(c, c.sa + c.a_off, c.sa + IMG_W2L, true)));
-  epi_hidden<256, false>(c, ES_B2);
-  ETC_LAYER((issue<16, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W3)); (issue<16, 32, 32>(c, c.sa + c.a_off, c.sa + IMG_W3L, true)));
-  const uint32_t tbase = c.tmem + ((uint32_t)(c.row & ~31) << 16);
-  tmem_ld16(tbase + 16 * c.part, out16);
+  mbar_wait(c.wbar, 0);                                           // completes once; later calls return immediately
+  const uint32_t X = c.tmem + TM_X, Y = c.tmem + TM_Y, Z = c.tmem + TM_Z;
+  ETC_LAYER((issue3_packed<1, 32, 32, 1>(X, Y, c.sa + IMG_W0)));                                        // 6 -> 32
+  epi_hidden<32>(c, ES_B0, TM_Y);
+  ETC_LAYER((issue3_packed<2, 64, 64, 2>(X, Y, c.sa + IMG_W1)));                                        // 32 -> 64
+  epi_hidden<64>(c, ES_B1, TM_Y);
+  ETC_LAYER((issue3<4, 128, 256, 0, 0>(X, Y, c.sa + IMG_W2H, c.sa + IMG_W2L, false)));                  // 64 -> 256, outputs 0..127
+  epi_hidden<128>(c, ES_B2, TM_X);                                                                      //   in place: layer-3 operand, K 0..127
+  ETC_LAYER((issue3<8, 32, 32, 0, 0>(Z, X, c.sa + IMG_W3H, c.sa + IMG_W3L, false)));                    // 256 -> 29, K 0..127
+  ETC_LAYER((issue3<4, 128, 256, 0, 128>(X, Y, c.sa + IMG_W2H, c.sa + IMG_W2L, false)));                // 64 -> 256, outputs 128..255
+  epi_hidden<128>(c, ES_B2 + 128, TM_X);
+  ETC_LAYER((issue3<8, 32, 32, 8, 0>(Z, X, c.sa + IMG_W3H, c.sa + IMG_W3L, true)));                     // 256 -> 29, K 128..255
+  tmem_ld16(lane_base(c) + TM_Z + 16 * c.part, out16);
 #pragma unroll
   for (int i = 0; i < 16; ++i) out16[i] += sm[ES_B3 + 16 * c.part + i];
 }
 
 template <bool SCATTER>
-__global__ void __launch_bounds__(CTA_T, 1) encoder_kernel(const Sample* __restrict__ samples, const float* __restrict__ x6, int m_host,
+__global__ void __launch_bounds__(CTA_T, 2) encoder_kernel(const Sample* __restrict__ samples, const float* __restrict__ x6, int m_host,
                                                            const int* __restrict__ m_dev, const void* __restrict__ blob,
                                                            float* __restrict__ out) {
   Ctx c;
   prologue(c, blob);
   const int m = m_dev ? *m_dev : m_host;
-  for (long long tile = (long long)blockIdx.x * GROUPS + c.grp; tile * T < m; tile += (long long)gridDim.x * GROUPS) {
+  for (long long tile = blockIdx.x; tile * T < m; tile += gridDim.x) {
     const int i = (int)(tile * T) + c.row;
     const bool valid = i < m;
     float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -233,26 +232,29 @@ __global__ void __launch_bounds__(CTA_T, 1) encoder_kernel(const Sample* __restr
         }
       }
     }
+    // the next tile's layer-0 operand goes to Y, which layer 2b read last: its MMA has completed (waited above); Z is read
+    // by this thread only
   }
+  mbar_wait(c.wbar, 0);                       // a CTA without tiles must not exit with its bulk copies in flight
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
+  if (threadIdx.x < 32) tmem_dealloc(c.tmem, TMEM_COLS);
 }
 
 }  // namespace etc
 
+static int enc_grid(long long m) { return (int)std::min<long long>(div_up(m, etc::T), 2LL * sm_count()); }
+
 int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, float* acc, cudaStream_t s) {
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
-  const int grid = (int)std::min<long long>(div_up(m_max, etc::T * etc::GROUPS), (long long)sm_count());
-  etc::encoder_kernel<true><<<grid, etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev, tc_blob, acc);
+  etc::encoder_kernel<true><<<enc_grid(m_max), etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev, tc_blob, acc);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
 
 int tc_encoder_explicit(const float* x6, int m, const void* tc_blob, float* out, cudaStream_t s) {
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
-  const int grid = (int)std::min<long long>(div_up(m, etc::T * etc::GROUPS), (long long)sm_count());
-  etc::encoder_kernel<false><<<grid, etc::CTA_T, etc::SM_ALLOC, s>>>(nullptr, x6, m, nullptr, tc_blob, out);
+  etc::encoder_kernel<false><<<enc_grid(m), etc::CTA_T, etc::SM_ALLOC, s>>>(nullptr, x6, m, nullptr, tc_blob, out);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -353,7 +353,7 @@ static int encoder_engine() {
   }
   return g_enc_engine;
 }
-constexpr int ENC_TC_BLOB_BYTES = 155648 + 2048;   // encoder_tc.cu: etc::BLOB_BYTES
+constexpr int ENC_TC_BLOB_BYTES = 110592 + 2048;   // encoder_tc.cu: etc::BLOB_BYTES
 
 extern "C" {
 

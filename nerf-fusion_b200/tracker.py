@@ -76,6 +76,8 @@ class SDFTracker:
         self._fe_graphs = {}               # key -> dict(graph, static inputs/outputs)
         self._fe_ws = {}                   # depth shape -> workspace owned by the front end (its address is baked into the graphs)
         self._fe_seen = {}                 # key -> eager calls so far (the first call warms kernels and workspaces up)
+        self._fe_busy = {}                 # key -> graph set whose static outputs last_intensity / last_depth still alias
+        self._fe_choice = None             # (key, set) the last graphed front-end call replayed
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
         self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()       # DFB_GN_PINNED_DOUBLES
@@ -139,15 +141,20 @@ class SDFTracker:
 
     def _frontend_graphed(self, rgb_data, depth_data, calib, depth_cut=None):
         """Replays the captured front end on copies of the inputs.  The first call per key runs eagerly (loads kernels,
-        sizes workspaces); later calls capture / replay.  Two graphs per key alternate (their outputs are static buffers,
-        and the pyramids of frame t are still read as `last_*` while frame t+1 is processed)."""
+        sizes workspaces); later calls capture / replay.  Two graph sets per key exist because their outputs are static
+        buffers and the pyramids of the last COMMITTED frame are still read as `last_*` while the next frame is processed:
+        a call replays the set `last_*` does not alias (track_camera marks a set busy when it commits its pyramids), so
+        calls that commit nothing (for_pc=True, a failed solve) can never make a frame's photometric term read itself."""
         base = (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode,
                 None if depth_cut is None else tuple(depth_cut))
         seen = self._fe_seen.get(base, 0)
         self._fe_seen[base] = seen + 1
+        self._fe_choice = None
         if seen == 0:
             return self._frontend(rgb_data, depth_data, calib, depth_cut)
-        key = base + (seen & 1,)
+        idx = 1 if self._fe_busy.get(base) == 0 else 0
+        self._fe_choice = (base, idx)
+        key = base + (idx,)
         ent = self._fe_graphs.get(key)
         if ent is None:
             ent = dict(rgb=torch.empty_like(rgb_data), depth=torch.empty_like(depth_data))
@@ -220,14 +227,20 @@ class SDFTracker:
             final_pose = self.gauss_newton(self.all_pd_pose[-1].dot(Isometry()), cur_intensity, cur_depth, cur_dIdxy, pc_data, calib)
         self.last_intensity = cur_intensity
         self.last_depth = cur_depth
+        if graphed:
+            if self._fe_choice is not None:            # last_* now alias this set's static outputs
+                self._fe_busy[self._fe_choice[0]] = self._fe_choice[1]
+            else:                                      # eager outputs are fresh tensors: no set is aliased any more
+                self._fe_busy.clear()
         self.all_pd_pose.append(final_pose)
         return final_pose
 
     # ------------------------------------------------------------------------------------------ GN terms
     def _read_hg(self, scale_of_count):
         """Copies the 44 result doubles to pinned host memory and unpacks (H, g, sum_wr2, count)."""
-        self._hg_host.copy_(self._hg_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.device(self.map.device):
+            self._hg_host.copy_(self._hg_dev, non_blocking=True)
+            torch.cuda.current_stream(self.map.device).synchronize()
         v = self._hg_host.numpy()
         return v[:36].reshape(6, 6).copy(), v[36:42].copy(), float(v[42]), float(v[43])
 

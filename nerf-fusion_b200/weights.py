@@ -128,19 +128,16 @@ def pack_encoder(W):
 
 def pack_encoder_tc(w0, b0, w1, b1, w2, b2, w3, b3):
     """FP16 SWIZZLE_128B images + FP32 biases for the tcgen05 encoder engine (csrc/encoder_tc.cu IMG_* / ES_*).
-    Every matrix is split hi = fp16(W), lo = fp16(W - hi); the hi image of layers 0..2 is duplicated under the
-    [hi | lo] halves of the split activations, the lo image sits under the hi half only."""
+    Every matrix is split hi = fp16(W), lo = fp16(W - hi); the engine computes A_hi W_hi + A_lo W_hi + A_hi W_lo.
+    Layers 0 and 1 keep hi and lo side by side in one 64-column block (lo at K step 1 / 2), layers 2 and 3 as two images."""
     def h(m):
         return m.astype(np.float16).astype(np.float32)
     w3p = np.zeros((32, 256), np.float32); w3p[:29] = w3
-    i0 = np.zeros((32, 64), np.float32); i0[:, 0:6] = h(w0); i0[:, 8:14] = h(w0)
-    i1 = np.concatenate([h(w1), h(w1)], axis=1)                                      # (64, 64)
-    i2 = np.concatenate([h(w2), h(w2)], axis=1)                                      # (256, 128)
-    l0 = np.zeros((32, 64), np.float32); l0[:, 0:6] = w0 - h(w0)
-    l1 = np.zeros((64, 64), np.float32); l1[:, :32] = w1 - h(w1)
-    mats = [i0, i1, i2, h(w3p), l0, l1, w2 - h(w2), w3p - h(w3p)]
+    i0 = np.zeros((32, 64), np.float32); i0[:, 0:6] = h(w0); i0[:, 16:22] = w0 - h(w0)
+    i1 = np.concatenate([h(w1), w1 - h(w1)], axis=1)                                 # (64, 64)
+    mats = [i0, i1, h(w2), w2 - h(w2), h(w3p), w3p - h(w3p)]
     img = np.concatenate([_swizzled_image(m) for m in mats]).view(np.uint8)
-    assert img.size == 155648, img.size
+    assert img.size == 110592, img.size
     sm = np.zeros(2048 // 4, np.float32)
     sm[0:32] = b0; sm[32:96] = b1; sm[96:352] = b2; sm[352:381] = b3
     return np.concatenate([img, sm.view(np.uint8)])

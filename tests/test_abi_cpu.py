@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_only_entry_points():
     lib = pkg()._lib.load()
     assert lib.dfb_version() >= 100
-    assert lib.dfb_decoder_blob_floats() == 91624 + 50688 and lib.dfb_encoder_blob_floats() == 27264 + 39424
+    assert lib.dfb_decoder_blob_floats() == 91624 + 50688 and lib.dfb_encoder_blob_floats() == 27264 + 28160
     for n in (0, 1, 77000):
         assert lib.dfb_pcproc_ws_bytes(n) > 0 and lib.dfb_box_filter_ws_bytes(n) > 0
         assert lib.dfb_integrate_ws_bytes(n, 256000) >= n * (12 + 4 + 8 * 32)

@@ -14,12 +14,10 @@ DEV = "cuda:0"
 
 
 @pytest.fixture(autouse=True)
-def _fp32_engine():
-    """Exact-parity tests use the FP32 CUDA-core decoder engine; tests/test_gpu_tc.py covers the tcgen05 engine."""
-    lib = pkg()._lib.load()
-    lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
-    yield
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
+def _engines(use_engine):
+    """Every test of this module runs under both engine configurations (tests/conftest.py): the default tcgen05 engines that
+    bench.py measures, and the FP32 CUDA-core pair."""
+    yield use_engine
 
 
 @pytest.fixture(scope="module")
@@ -27,7 +25,7 @@ def G():
     return dict(np.load(GOLD / "map_golden.npz"))
 
 
-def _check_state(m, G, tag):
+def _check_state(m, G, tag, engine):
     n = int(G[f"{tag}_n_occupied"])
     assert m.n_occupied == n
     assert m.latent_vecs.size(0) == int(G[f"{tag}_capacity"])
@@ -38,8 +36,9 @@ def _check_state(m, G, tag):
     assert (idx != -1).sum() == n
     assert np.array_equal(m.voxel_obs_count[:n].cpu().numpy(), G[f"{tag}_count"])
     lat, ref = m.latent_vecs[:n].cpu().numpy(), G[f"{tag}_latent"]
-    assert np.abs(lat - ref).max() <= 1e-3 * np.abs(ref).max()
-    assert np.abs(lat - ref).max() < 5e-6
+    assert np.abs(lat - ref).max() <= 1e-3 * np.abs(ref).max()              # north star: 1e-3 relative
+    if engine == "fp32":
+        assert np.abs(lat - ref).max() < 5e-6
     assert np.array_equal(m.mesh_cache.updated_vec_id.cpu().numpy(), G[f"{tag}_updated"])
     # zero-invariant scratch restored
     assert int(m._grid_count.abs().sum()) == 0 and int(m._grid_bits.abs().sum()) == 0
@@ -47,16 +46,18 @@ def _check_state(m, G, tag):
 
 
 @pytest.fixture(scope="module")
-def gmap(weights, G):
-    pkg()._lib.load().dfb_set_decoder_engine(0); pkg()._lib.load().dfb_set_encoder_engine(0)
+def gmap(weights, G, engine):
+    from conftest import ENGINES
+    lib = pkg()._lib.load()
+    lib.dfb_set_decoder_engine(ENGINES[engine][0]); lib.dfb_set_encoder_engine(ENGINES[engine][1])
     m = make_map(weights)
     Pw, Nw = torch.from_numpy(G["Pw"]).to(DEV), torch.from_numpy(G["Nw"]).to(DEV)
     mask1 = m.integrate_keyframe(Pw, Nw)
     assert np.array_equal(mask1.cpu().numpy(), G["k1_mask"])
-    _check_state(m, G, "k1")
+    _check_state(m, G, "k1", engine)
     mask2 = m.integrate_keyframe(Pw + torch.from_numpy(G["k2_shift"]).to(DEV), Nw)
     assert np.array_equal(mask2.cpu().numpy(), G["k2_mask"])
-    _check_state(m, G, "k2")
+    _check_state(m, G, "k2", engine)
     return m
 
 
@@ -234,13 +235,11 @@ def test_integrate_edge_cases(weights):
     (2, 0.25, [0.0, 0.0, 0.0], [3.0, 2.0, 1.0], 0),            # pruning disabled (unq_mask is None, map.py:373-374)
     (3, 0.05, [-0.4, -0.4, -0.4], [0.4, 0.4, 0.4], 30),
 ])
-@pytest.mark.parametrize("enc_engine", [0, 1])
-def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, prune, enc_engine):
+def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, prune):
     """Random surfaces in random grids (different voxel sizes, non-cubic extents, pruning thresholds, points on the
     grid border): masks, voxel ids, slot order and counts bit-exact against the CPU oracle over three keyframes,
     including voxels that cross the encoder_count_th = 600 threshold and stop being candidates.  Latents within the
     1e-3 relative north-star tolerance under both encoder engines (FP32 CUDA cores / tcgen05)."""
-    pkg()._lib.load().dfb_set_encoder_engine(enc_engine)
     rng = np.random.RandomState(seed)
     over = dict(bound_min=bmin, bound_max=bmax, voxel_size=voxel, prune_min_vox_obs=prune, encoder_count_th=120.0)
     m = make_map(weights, **over)

@@ -11,12 +11,10 @@ DEV = "cuda:0"
 
 
 @pytest.fixture(autouse=True)
-def _fp32_engine():
-    """Exact-parity tests use the FP32 CUDA-core decoder engine; tests/test_gpu_tc.py covers the tcgen05 engine."""
-    lib = pkg()._lib.load()
-    lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
-    yield
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
+def _engines(use_engine):
+    """Every test of this module runs under both engine configurations (tests/conftest.py): the default tcgen05 engines that
+    bench.py measures, and the FP32 CUDA-core pair."""
+    yield use_engine
 
 
 def _depth_frame(H=240, W=320, seed=0):

@@ -11,12 +11,10 @@ DEV = "cuda:0"
 
 
 @pytest.fixture(autouse=True)
-def _fp32_engine():
-    """Exact-parity tests use the FP32 CUDA-core decoder engine; tests/test_gpu_tc.py covers the tcgen05 engine."""
-    lib = pkg()._lib.load()
-    lib.dfb_set_decoder_engine(0); lib.dfb_set_encoder_engine(0)
-    yield
-    lib.dfb_set_decoder_engine(1); lib.dfb_set_encoder_engine(1)
+def _engines(use_engine):
+    """Every test of this module runs under both engine configurations (tests/conftest.py): the default tcgen05 engines that
+    bench.py measures, and the FP32 CUDA-core pair."""
+    yield use_engine
 
 
 @pytest.fixture(scope="module")
@@ -143,7 +141,41 @@ def test_graph_front_end_equals_eager(weights, T):
         for a, b in zip(out_g[0] + out_g[1] + out_g[2], out_e[0] + out_e[1] + out_e[2]):      # pyramids, gradients
             assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
         assert torch.equal(out_g[3][:n_g], out_e[3][:n_e]) and torch.equal(out_g[4][:n_g], out_e[4][:n_e])
-    assert len(trk_g._fe_graphs) == 2
+    assert len(trk_g._fe_graphs) == 1          # nothing was committed: the set `last_*` does not alias is always set 0
+
+
+def test_graph_front_end_with_uncommitted_calls(weights, T):
+    """A call that commits no pose (for_pc=True) between tracked frames must not make the next frame's photometric term
+    read the frame against itself: the graphed front end replays the set `last_*` does not alias.  Same poses as the
+    eager front end on a sequence that interleaves such calls."""
+    d = pkg()
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    first = d.Isometry(q=d.Quaternion(array=d.synth.FIRST_TQ[3:]), t=np.array(d.synth.FIRST_TQ[:3]))
+    cfg = dict(TRACKING)
+    cfg["iter_config"] = [{"n": 3, "type": [["rgb", 2]]}, {"n": 3, "type": [["sdf"], ["rgb", 1]]}, {"n": 8, "type": [["sdf"], ["rgb", 0]]}]
+    plan = [(0, "set"), (1, "track"), (2, "pc"), (2, "track"), (0, "pc"), (1, "pc"), (1, "track"), (2, "pc"), (2, "track")]
+    out = {}
+    for graph in (True, False):
+        m = make_map(weights)
+        trk = d.SDFTracker(m, ns(cfg))
+        trk.graph_frontend = graph
+        poses = []
+        for i, what in plan:
+            rgb, depth = _frame(T, i)
+            if what == "pc":
+                trk.track_camera(rgb, depth, calib, for_pc=True)
+                continue
+            pose = trk.track_camera(rgb, depth, calib, first if what == "set" else None)
+            if what == "set":
+                pc, nrm = trk.last_processed_pc
+                m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+            poses.append((pose.q.rotation_matrix.copy(), pose.t.copy()))
+        out[graph] = (poses, trk.n_rgb_evals)
+    assert out[True][1] == out[False][1]
+    for (Ra, ta), (Rb, tb) in zip(out[True][0], out[False][0]):
+        assert np.abs(Ra - Rb).max() < 1e-5 and np.abs(ta - tb).max() < 1e-5
+    # and the photometric term did see two different frames: the tracked poses moved
+    assert np.abs(out[True][0][1][1] - out[True][0][0][1]).max() > 1e-3
 
 
 def test_pose_parity_on_the_reference_points(weights, T):

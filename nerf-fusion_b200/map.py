@@ -394,6 +394,8 @@ class DenseIndexedMap:
                                np.clip(1.5 - np.abs(4 * c - 1), 0, 1)], axis=1)                    # jet colour map
         try:
             import open3d as o3d
+            if not hasattr(o3d.geometry, "TriangleMesh"):          # a stub / partial install: fall back to SimpleMesh
+                raise ImportError("open3d.geometry.TriangleMesh")
             mesh = o3d.geometry.TriangleMesh()
             mesh.vertices = o3d.utility.Vector3dVector(vertices.astype(float))
             mesh.triangles = o3d.utility.Vector3iVector(triangles.astype(np.int32))

@@ -84,6 +84,11 @@ def main():
     res["reference_cuda"] = dict(frames_per_s=float(len(ms) / (ms.sum() * 1e-3)), frame_ms_median=float(np.median(ms)),
                                  frame_ms=[round(float(x), 2) for x in ms], n_sdf=ref_run["n_sdf"], n_rgb=ref_run["n_rgb"],
                                  n_points=ref_run["n_points"], n_occupied=ref_run["map"]["n_occupied"])
+    # the reference against ITSELF: its kd-tree / scatter kernels use atomics, and the accept / rollback rule of its
+    # Gauss-Newton loop (tracker.py:269) compares energies that differ in the last digits, so two runs of the unmodified
+    # reference on identical inputs do not give identical poses or maps.  This is the floor any parity number sits on.
+    ref_again = C1.run_reference(frames, calib, dev, itc, keep_clouds=False)
+    res["reference_run_to_run"] = C1.compare(ref_again, ref_run)
     gt_err = max(float(np.abs(p[1] - seq.poses[i][1]).max()) for i, p in enumerate(ref_run["poses"]))
     res["reference_cuda"]["max_err_vs_ground_truth_m"] = gt_err
     for eng, name in ((1, "ours_tc"), (0, "ours_fp32")):

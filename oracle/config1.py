@@ -195,4 +195,60 @@ def compare(a, b):
         out["count_equal_frac"] = float((ma["count"][ia] == mb["count"][ib]).mean())
     if "n_points" in a and "n_points" in b:
         out["n_points_max_diff"] = int(max(abs(x - y) for x, y in zip(a["n_points"], b["n_points"])))
+    if a.get("clouds") and b.get("clouds"):                       # preprocessed clouds, frame by frame (same order in both paths)
+        pd, nd, rows = 0.0, 0.0, 0.0
+        for (pa, na), (pb, nb) in zip(a["clouds"], b["clouds"]):
+            if pa.shape != pb.shape:
+                continue
+            dp = (pa - pb).abs().max(1).values; dn = (na - nb).abs().max(1).values
+            pd = max(pd, float(dp.max())); nd = max(nd, float(dn.max()))
+            rows = max(rows, float(((dp > 1e-6) | (dn > 1e-4)).float().mean()))
+        out["cloud_point_max_abs"] = pd; out["cloud_normal_max_abs"] = nd; out["cloud_rows_differing_frac_max"] = rows
+    return out
+
+
+def decoder_deltas_on_reference_map(ref_run, dev, engines=(1, 0)):
+    """Reference map -> our map (cold_vars file), then get_sdf / compute_sdf_Hg of both engines vs the reference's."""
+    import tempfile
+    from pathlib import Path
+    dfb = dfb_pkg()
+    lib = dfb._lib.load()
+    rmap, rtrk = ref_run["map_obj"], ref_run["tracker_obj"]
+    ref = ref_gpu.install("reference")
+    m, trk = make_ours(dev)
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "map.pt"
+        rmap.save(p)
+        m.load(p)
+    pc = ref_run["clouds"][1][0]
+    last_R, last_t = ref_run["poses"][0]
+    xi = np.array([0.004, -0.003, 0.005, 0.002, -0.0015, 0.001])
+    r_last = ref.motion.Isometry(q=ref.Quaternion(matrix=last_R), t=last_t)
+    r_delta = ref.motion.Isometry.from_twist(xi)
+    o_last = dfb.Isometry.from_matrix(last_R, last_t)
+    o_delta = dfb.Isometry.from_twist(xi)
+    Hr, gr, er = rtrk.compute_sdf_Hg(0, r_last, r_delta, pc)
+    world = (r_last.dot(r_delta)) @ pc
+    with torch.no_grad():
+        sr, dr, vr = rmap.get_sdf(world)
+    out = {}
+    for eng in engines:
+        lib.dfb_set_decoder_engine(eng)
+        Ho, go, eo = trk.compute_sdf_Hg(0, o_last, o_delta, pc.contiguous())
+        so, do, vo = m.get_sdf(world.contiguous())
+        vr_ = vr.cpu().numpy().astype(bool); vo_ = vo.cpu().numpy().astype(bool)
+        both = vr_ & vo_
+        sdf_ref = np.zeros(len(vr_), np.float32); sdf_ref[vr_] = sr.detach().cpu().numpy().reshape(-1)
+        std_ref = np.zeros(len(vr_), np.float32); std_ref[vr_] = dr.detach().cpu().numpy().reshape(-1)
+        so_ = so.detach().cpu().numpy().reshape(-1); do_ = do.detach().cpu().numpy().reshape(-1)
+        if so_.shape[0] != len(vr_):                       # compact outputs
+            t = np.zeros(len(vr_), np.float32); t[vo_] = so_; so_ = t
+            t = np.zeros(len(vr_), np.float32); t[vo_] = do_; do_ = t
+        out[f"engine{eng}"] = dict(
+            H_rel=float(np.abs(Ho - Hr).max() / np.abs(Hr).max()), g_rel=float(np.abs(go - gr).max() / np.abs(gr).max()),
+            E_rel=float(abs(eo - er) / abs(er)), valid_equal=bool(np.array_equal(vr_, vo_)),
+            sdf_max_abs_network_units=float(np.abs(so_[both] - sdf_ref[both]).max()),
+            sdf_max_abs_m=float(np.abs(so_[both] - sdf_ref[both]).max() * 0.1),
+            std_max_abs=float(np.abs(do_[both] - std_ref[both]).max()), n_queries=int(len(vr_)), n_valid=int(both.sum()))
+    lib.dfb_set_decoder_engine(1)
     return out

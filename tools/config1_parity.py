@@ -10,7 +10,6 @@ reference's map (loaded into this repo's map through the shared cold_vars file f
 import argparse
 import json
 import sys
-import tempfile
 from pathlib import Path
 
 import numpy as np
@@ -19,50 +18,6 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from oracle import config1 as C1, ref_gpu  # noqa: E402
-
-
-def engine_deltas(dfb, ref_run, frames, calib, dev):
-    """Reference map -> our map (cold_vars file), then get_sdf / compute_sdf_Hg of both engines vs the reference's."""
-    lib = dfb._lib.load()
-    rmap, rtrk = ref_run["map_obj"], ref_run["tracker_obj"]
-    ref = ref_gpu.install("reference")
-    m, trk = C1.make_ours(dev)
-    with tempfile.TemporaryDirectory() as td:
-        p = Path(td) / "map.pt"
-        rmap.save(p)
-        m.load(p)
-    pc = ref_run["clouds"][1][0]
-    last_R, last_t = ref_run["poses"][0]
-    xi = np.array([0.004, -0.003, 0.005, 0.002, -0.0015, 0.001])
-    r_last = ref.motion.Isometry(q=ref.Quaternion(matrix=last_R), t=last_t)
-    r_delta = ref.motion.Isometry.from_twist(xi)
-    o_last = dfb.Isometry.from_matrix(last_R, last_t)
-    o_delta = dfb.Isometry.from_twist(xi)
-    Hr, gr, er = rtrk.compute_sdf_Hg(0, r_last, r_delta, pc)
-    world = (r_last.dot(r_delta)) @ pc
-    with torch.no_grad():
-        sr, dr, vr = rmap.get_sdf(world)
-    out = {}
-    for eng in (1, 0):
-        lib.dfb_set_decoder_engine(eng)
-        Ho, go, eo = trk.compute_sdf_Hg(0, o_last, o_delta, pc.contiguous())
-        so, do, vo = m.get_sdf(world.contiguous())
-        vr_ = vr.cpu().numpy().astype(bool); vo_ = vo.cpu().numpy().astype(bool)
-        both = vr_ & vo_
-        sdf_ref = np.zeros(len(vr_), np.float32); sdf_ref[vr_] = sr.detach().cpu().numpy().reshape(-1)
-        std_ref = np.zeros(len(vr_), np.float32); std_ref[vr_] = dr.detach().cpu().numpy().reshape(-1)
-        so_ = so.detach().cpu().numpy().reshape(-1); do_ = do.detach().cpu().numpy().reshape(-1)
-        if so_.shape[0] != len(vr_):                       # compact outputs
-            t = np.zeros(len(vr_), np.float32); t[vo_] = so_; so_ = t
-            t = np.zeros(len(vr_), np.float32); t[vo_] = do_; do_ = t
-        out[f"engine{eng}"] = dict(
-            H_rel=float(np.abs(Ho - Hr).max() / np.abs(Hr).max()), g_rel=float(np.abs(go - gr).max() / np.abs(gr).max()),
-            E_rel=float(abs(eo - er) / abs(er)), valid_equal=bool(np.array_equal(vr_, vo_)),
-            sdf_max_abs_network_units=float(np.abs(so_[both] - sdf_ref[both]).max()),
-            sdf_max_abs_m=float(np.abs(so_[both] - sdf_ref[both]).max() * 0.1),
-            std_max_abs=float(np.abs(do_[both] - std_ref[both]).max()), n_queries=int(len(vr_)), n_valid=int(both.sum()))
-    lib.dfb_set_decoder_engine(1)
-    return out
 
 
 def main():
@@ -87,14 +42,14 @@ def main():
     # the reference against ITSELF: its kd-tree / scatter kernels use atomics, and the accept / rollback rule of its
     # Gauss-Newton loop (tracker.py:269) compares energies that differ in the last digits, so two runs of the unmodified
     # reference on identical inputs do not give identical poses or maps.  This is the floor any parity number sits on.
-    ref_again = C1.run_reference(frames, calib, dev, itc, keep_clouds=False)
+    ref_again = C1.run_reference(frames, calib, dev, itc, keep_clouds=True)
     res["reference_run_to_run"] = C1.compare(ref_again, ref_run)
     gt_err = max(float(np.abs(p[1] - seq.poses[i][1]).max()) for i, p in enumerate(ref_run["poses"]))
     res["reference_cuda"]["max_err_vs_ground_truth_m"] = gt_err
     for eng, name in ((1, "ours_tc"), (0, "ours_fp32")):
         lib.dfb_set_decoder_engine(eng)
         C1.run_ours(frames[:4], calib, dev, itc)                               # warm-up (graphs captured per tracker, kernels loaded)
-        run = C1.run_ours(frames, calib, dev, itc)
+        run = C1.run_ours(frames, calib, dev, itc, keep_clouds=True)
         ms = np.array(run["frame_ms"])
         res[name] = dict(frames_per_s=float(len(ms) / (ms.sum() * 1e-3)), frame_ms_median=float(np.median(ms)), n_sdf=run["n_sdf"],
                          n_rgb=run["n_rgb"], n_points=run["n_points"], vs_reference=C1.compare(run, ref_run),
@@ -103,7 +58,7 @@ def main():
         res[name]["on_reference_points"] = C1.compare(onref, ref_run)
         res[name]["on_reference_points"]["n_sdf"] = onref["n_sdf"]
     lib.dfb_set_decoder_engine(1)
-    res["decoder_vs_reference_on_reference_map"] = engine_deltas(dfb, ref_run, frames, calib, dev)
+    res["decoder_vs_reference_on_reference_map"] = C1.decoder_deltas_on_reference_map(ref_run, dev)
     # operator-level drop-in: the reference's unmodified map.py / tracker.py on this repo's ops
     try:
         drop = C1.run_reference(frames, calib, dev, itc, backend="dfb", keep_clouds=False)

@@ -258,6 +258,72 @@ int dfb_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
                        int B, int r, float max_std, int max_tri, float* tri, int64_t* flat_id, float* tri_std,
                        int32_t* d_n_tri, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sharded map (BASELINE config 5; new functionality, the reference has no multi-GPU map).
+ * integrate_keyframe of system/map.py:341-453 over the union of all ranks' points, voxel ids partitioned in 8^3 bricks dealt
+ * round-robin to the ranks.  Records travel by PEER STORES from the producing kernel into the owner's receive buffer
+ * (`peer_*[d]` = base of this rank's segment inside rank d's inbox; for d == rank it is the local inbox).  The host side
+ * (nerf-fusion_b200/sharded.py) owns the memory, maps the peers (dfb_peer_* below, CUDA IPC) and runs a stream-ordered
+ * barrier between the five phases; see csrc/sharded.cu for the protocol.  All pointers are device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+#define DFB_SHARD_MAX_WORLD 8
+typedef struct {
+  int32_t nx, ny, nz;
+  float bound_min[3];
+  float voxel_size;
+  int32_t div_mode, prune_min_vox_obs;
+  float encoder_count_th;
+  int32_t world, rank;
+  /* owned state */
+  int32_t* indexer_local;      /* dfb_shard_local_cells() ints, -1 = unallocated, else slot */
+  float* latent_vecs;          /* (capacity, 29), zero for unused slots */
+  int32_t* latent_vecs_pos;    /* (capacity,) linear voxel id of a slot */
+  float* voxel_obs_count;      /* (capacity,) */
+  int32_t capacity;
+  uint32_t* cand_bits;         /* ceil(nx ny nz / 32) words: candidate voxels (allocated, obs_count < encoder_count_th), all ranks' */
+  int32_t* grid_count;         /* dfb_shard_local_cells() ints, zero between keyframes */
+  float* acc;                  /* (capacity, 29) zero between keyframes */
+  int32_t* acc_n;              /* (capacity,) zero between keyframes */
+  int32_t* touched;            /* (capacity,) scratch */
+  int32_t* counters;           /* dfb_shard_counter_ints() ints, zero-initialised once; [3*8+3] = n_occupied */
+  int32_t* delta_list;         /* (delta_cap,) */
+  int32_t* next_delta;         /* (delta_cap,) */
+  int32_t* n_next_delta;       /* 1 int, zero-initialised */
+  int32_t delta_cap;
+  /* receive buffers of THIS rank: `world` segments each, segment s written by rank s */
+  void* pts_inbox;    int32_t pts_cap; int32_t* pts_count;   /* 32-byte point records; counts: `world` ints */
+  int32_t* ids_inbox; int32_t ids_cap; int32_t* ids_count;   /* 4-byte voxel ids (allocation requests) */
+  void* smp_inbox;    int32_t smp_cap; int32_t* smp_count;   /* 32-byte samples {id -> slot, rel[3], n[3]} */
+  int32_t* dlt_inbox; int32_t dlt_cap; int32_t* dlt_count;   /* 4-byte candidate-set deltas (id << 1 | removed) */
+  /* where THIS rank writes: its segment inside rank d's buffers, and rank d's count slot for this rank */
+  void* peer_pts[DFB_SHARD_MAX_WORLD]; int32_t* peer_pts_count[DFB_SHARD_MAX_WORLD];
+  void* peer_ids[DFB_SHARD_MAX_WORLD]; int32_t* peer_ids_count[DFB_SHARD_MAX_WORLD];
+  void* peer_smp[DFB_SHARD_MAX_WORLD]; int32_t* peer_smp_count[DFB_SHARD_MAX_WORLD];
+  void* peer_dlt[DFB_SHARD_MAX_WORLD]; int32_t* peer_dlt_count[DFB_SHARD_MAX_WORLD];
+} dfb_shard;
+
+int dfb_shard_counter_ints(void);
+int64_t dfb_shard_local_cells(int nx, int ny, int nz, int world);
+/* phase 1: this rank's share of the keyframe (n <= pts_cap points) -> owners of the home voxels.            [barrier] */
+int dfb_shard_phase1(const dfb_shard* S, const float* xyz, const float* normal, int n, void* stream);
+/* phase 2: count, prune (map.py:373-379), allocate home voxels + face neighbours (:382-388), request remote ones. [barrier] */
+int dfb_shard_phase2(const dfb_shard* S, void* stream);
+/* phase 3: allocate requested ids, broadcast this rank's candidate-set deltas.                              [barrier] */
+int dfb_shard_phase3(const dfb_shard* S, void* stream);
+/* phase 4: apply deltas, build the (point, offset) samples (map.py:390-436), push them to their voxels' owners. [barrier] */
+int dfb_shard_phase4(const dfb_shard* S, void* stream);
+/* phase 5: id -> slot, encoder on the receive buffer, running mean (map.py:446-452).  d_stats: 8 + 2*8 device ints
+ * {points received, samples received, voxels allocated, error bits, n_occupied, voxels updated, -, -, points sent to rank d..,
+ * samples sent to rank d..}. */
+int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_stats, void* stream);
+
+/* Peer-mappable device memory (cudaMalloc + CUDA IPC): alloc returns the pointer and a 64-byte handle another process on the
+ * same node opens with dfb_peer_open (peer access over NVLink is enabled lazily by the driver). */
+int dfb_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int dfb_peer_open(const unsigned char* handle64, void** ptr);
+int dfb_peer_close(void* ptr);
+int dfb_peer_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,28 @@ class RgbLevel(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32)]
 
 
+SHARD_MAX_WORLD = 8
+
+
+class Shard(C.Structure):
+    """dfb_shard (include/difusion_b200.h): one rank of the sharded map, all pointers are device pointers."""
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("bound_min", C.c_float * 3), ("voxel_size", C.c_float),
+                ("div_mode", C.c_int32), ("prune_min_vox_obs", C.c_int32), ("encoder_count_th", C.c_float),
+                ("world", C.c_int32), ("rank", C.c_int32),
+                ("indexer_local", C.c_void_p), ("latent_vecs", C.c_void_p), ("latent_vecs_pos", C.c_void_p), ("voxel_obs_count", C.c_void_p),
+                ("capacity", C.c_int32), ("cand_bits", C.c_void_p), ("grid_count", C.c_void_p), ("acc", C.c_void_p), ("acc_n", C.c_void_p),
+                ("touched", C.c_void_p), ("counters", C.c_void_p), ("delta_list", C.c_void_p), ("next_delta", C.c_void_p),
+                ("n_next_delta", C.c_void_p), ("delta_cap", C.c_int32),
+                ("pts_inbox", C.c_void_p), ("pts_cap", C.c_int32), ("pts_count", C.c_void_p),
+                ("ids_inbox", C.c_void_p), ("ids_cap", C.c_int32), ("ids_count", C.c_void_p),
+                ("smp_inbox", C.c_void_p), ("smp_cap", C.c_int32), ("smp_count", C.c_void_p),
+                ("dlt_inbox", C.c_void_p), ("dlt_cap", C.c_int32), ("dlt_count", C.c_void_p),
+                ("peer_pts", C.c_void_p * SHARD_MAX_WORLD), ("peer_pts_count", C.c_void_p * SHARD_MAX_WORLD),
+                ("peer_ids", C.c_void_p * SHARD_MAX_WORLD), ("peer_ids_count", C.c_void_p * SHARD_MAX_WORLD),
+                ("peer_smp", C.c_void_p * SHARD_MAX_WORLD), ("peer_smp_count", C.c_void_p * SHARD_MAX_WORLD),
+                ("peer_dlt", C.c_void_p * SHARD_MAX_WORLD), ("peer_dlt_count", C.c_void_p * SHARD_MAX_WORLD)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
@@ -82,6 +104,17 @@ SIGNATURES = {
     "dfb_decode_cubes_ws_bytes": (_SZ, [_I, _I]),
     "dfb_decode_cubes": (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
     "dfb_marching_cubes": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "dfb_shard_counter_ints": (_I, []),
+    "dfb_shard_local_cells": (_I64, [_I, _I, _I, _I]),
+    "dfb_shard_phase1": (_I, [C.POINTER(Shard), _P, _P, _I, _P]),
+    "dfb_shard_phase2": (_I, [C.POINTER(Shard), _P]),
+    "dfb_shard_phase3": (_I, [C.POINTER(Shard), _P]),
+    "dfb_shard_phase4": (_I, [C.POINTER(Shard), _P]),
+    "dfb_shard_phase5": (_I, [C.POINTER(Shard), _P, _P, _P]),
+    "dfb_peer_alloc": (_I, [_SZ, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "dfb_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "dfb_peer_close": (_I, [_P]),
+    "dfb_peer_free": (_I, [_P]),
 }
 
 # kernels (and memset nodes excluded) each entry point launches; used for the bench's `gpu_launches` claim
@@ -91,6 +124,7 @@ KERNELS_PER_CALL = {
     "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
     "gn_kernel": 1,                    # launched inside dfb_gauss_newton (count reported through h_stats[7])
+    "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4,
 }
 CALLS = {}
 

@@ -199,16 +199,38 @@ __device__ __forceinline__ void encode_tile(Ctx& c, const float in[6], float out
   for (int i = 0; i < 16; ++i) out16[i] += sm[ES_B3 + 16 * c.part + i];
 }
 
+// Input forms: explicit rows x6 (SCATTER = false), one contiguous sample array with its length on the device (m_dev), or --
+// for the sharded map -- N_SEG fixed-capacity segments of a receive buffer (segment s = rows [s seg_cap, s seg_cap +
+// seg_counts[s])), consumed in place: no compaction pass between the exchange and the encoder.
+constexpr int MAX_SEG = 8;
 template <bool SCATTER>
 __global__ void __launch_bounds__(CTA_T, 2) encoder_kernel(const Sample* __restrict__ samples, const float* __restrict__ x6, int m_host,
-                                                           const int* __restrict__ m_dev, const void* __restrict__ blob,
-                                                           float* __restrict__ out) {
+                                                           const int* __restrict__ m_dev, const int* __restrict__ seg_counts, int n_seg,
+                                                           int seg_cap, const void* __restrict__ blob, float* __restrict__ out) {
   Ctx c;
   prologue(c, blob);
-  const int m = m_dev ? *m_dev : m_host;
-  for (long long tile = blockIdx.x; tile * T < m; tile += gridDim.x) {
-    const int i = (int)(tile * T) + c.row;
-    const bool valid = i < m;
+  int cum[MAX_SEG + 1];                                  // tiles before segment s
+  cum[0] = 0;
+  if (n_seg > 0) {
+#pragma unroll
+    for (int sgi = 0; sgi < MAX_SEG; ++sgi) cum[sgi + 1] = cum[sgi] + (sgi < n_seg ? (min(seg_counts[sgi], seg_cap) + T - 1) / T : 0);
+  } else {
+    const int m = m_dev ? *m_dev : m_host;
+#pragma unroll
+    for (int sgi = 0; sgi < MAX_SEG; ++sgi) cum[sgi + 1] = (m + T - 1) / T;
+  }
+  const int m0 = n_seg > 0 ? 0 : (m_dev ? *m_dev : m_host);
+  for (int tile = blockIdx.x; tile < cum[MAX_SEG]; tile += gridDim.x) {
+    int seg = 0;
+#pragma unroll
+    for (int sgi = 1; sgi < MAX_SEG; ++sgi) seg += (n_seg > 0 && tile >= cum[sgi]) ? 1 : 0;
+    int base = 0;
+#pragma unroll
+    for (int sgi = 0; sgi < MAX_SEG; ++sgi) base = (sgi == seg) ? cum[sgi] : base;
+    const int il = (tile - base) * T + c.row;                                  // row inside the segment (or the whole input)
+    const int m = n_seg > 0 ? min(seg_counts[seg], seg_cap) : m0;
+    const bool valid = il < m;
+    const long long i = n_seg > 0 ? (long long)seg * seg_cap + il : il;
     float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int slot = 0;
     if (valid) {
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(CTA_T, 2) encoder_kernel(const Sample* __restr
     }
     float o[16];
     encode_tile(c, in, o);
-    if (valid) {
+    if (valid && slot >= 0) {
       float* dst = out + (size_t)(SCATTER ? slot : i) * DFB_LATENT_DIM + 16 * c.part;
 #pragma unroll
       for (int l = 0; l < 16; ++l) {
@@ -247,14 +269,26 @@ static int enc_grid(long long m) { return (int)std::min<long long>(div_up(m, etc
 
 int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, float* acc, cudaStream_t s) {
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
-  etc::encoder_kernel<true><<<enc_grid(m_max), etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev, tc_blob, acc);
+  etc::encoder_kernel<true><<<enc_grid(m_max), etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev,
+                                                                            nullptr, 0, 0, tc_blob, acc);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// sharded map: the samples are the segments of the exchange's receive buffer (sharded.cu)
+int tc_encoder_scatter_segments(const void* samples, const int* seg_counts, int n_seg, int seg_cap, const void* tc_blob, float* acc,
+                                cudaStream_t s) {
+  if (n_seg < 1 || n_seg > etc::MAX_SEG) { set_error("encoder: 1..%d segments", etc::MAX_SEG); return DFB_E_INVALID; }
+  DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
+  etc::encoder_kernel<true><<<enc_grid((long long)n_seg * seg_cap), etc::CTA_T, etc::SM_ALLOC, s>>>(
+      reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, nullptr, seg_counts, n_seg, seg_cap, tc_blob, acc);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
 
 int tc_encoder_explicit(const float* x6, int m, const void* tc_blob, float* out, cudaStream_t s) {
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
-  etc::encoder_kernel<false><<<enc_grid(m), etc::CTA_T, etc::SM_ALLOC, s>>>(nullptr, x6, m, nullptr, tc_blob, out);
+  etc::encoder_kernel<false><<<enc_grid(m), etc::CTA_T, etc::SM_ALLOC, s>>>(nullptr, x6, m, nullptr, nullptr, 0, 0, tc_blob, out);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

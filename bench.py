@@ -319,6 +319,29 @@ def run_ours(args):
     # third timed region, same K frames: CUDA events around every launch of the dominant kernel (roofline numbers only;
     # the per-launch event synchronisation costs ~5 % of the frame, so it is kept out of the two throughput passes)
     res_k = run(e2e=False, time_kernels=True)
+    # BASELINE config 5 (the path that actually communicates): the spatially sharded map, 1 M-point keyframes, ~4 M voxels,
+    # records pushed into the owners' receive buffers over NVLink (csrc/sharded.cu); measured in this same launch
+    sharded = None
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import sharded_bench
+    except Exception as e:
+        sharded = {"unavailable": repr(e)[:200]}
+    if sharded is None:
+        try:
+            torch.cuda.empty_cache()
+            if world > 1:
+                import torch.distributed as dist
+                one = sharded_bench.run(parity=False, force_world1=True) if rank == 0 else None      # N = 1 baseline on rank 0's GPU
+                dist.barrier()
+                sharded = sharded_bench.run(parity=True)
+                if rank == 0:
+                    sharded["points_per_s_1gpu_same_run"] = one["points_per_s"]
+                    sharded["efficiency_vs_1gpu"] = round(sharded["points_per_s"] / (world * one["points_per_s"]), 4)
+            else:
+                sharded = sharded_bench.run(parity=True)
+        except Exception as e:
+            sharded = {"unavailable": repr(e)[:300]}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -337,7 +360,7 @@ def run_ours(args):
                    "sdf_gn_evals_per_frame": round(res["sdf_evals"] / n_frames, 1), "rgb_gn_evals_per_frame": round(res["rgb_evals"] / n_frames, 1),
                    "l2": "flushed before every frame (192 MiB write)", "parallelism": "replicas" if world > 1 else "single",
                    "max_track_err_m": round(res["track_err"], 5), "timed_by": "cuda events around the K-frame loop, max over ranks",
-                   "wall_s": round(res["wall"], 3)},
+                   "wall_s": round(res["wall"], 3), "sharded": sharded},
         "clocks": res["clocks"],
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 # per frame the host reads: a 16-byte record per evaluation (incl. one look-ahead launch per group), the

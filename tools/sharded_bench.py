@@ -2,7 +2,7 @@
 over NVLink (csrc/sharded.cu).  Run under torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_bench.py
 or with N = 1 directly.  Each keyframe = `--points` points (split evenly over the ranks) on a wavy floor patch of a
-40 x 10 x 40 m volume at 0.05 m voxels (128 M cells; two storeys of 4 x 4 patches: ~4 M voxels allocated over 32 keyframes).  Reports points/s integrated (device
+40 x 10 x 40 m volume at 0.05 m voxels (128 M cells; three storeys of 4 x 4 patches: > 4 M voxels allocated over 48 keyframes).  Reports points/s integrated (device
 time, max over ranks), peer-store bytes, and checks the sharded state against a single-GPU DenseIndexedMap (rank 0).
 bench.py imports `run()` for its N > 1 line."""
 import argparse, importlib, json, os, sys
@@ -23,12 +23,13 @@ def scene_points(n, seed, lo, hi, dev, y0=1.0):
     return torch.stack([x, y, z], 1).contiguous(), nrm.contiguous()
 
 
-def run(points=1_000_000, keyframes=32, voxel=0.05, parity=True):
-    """Collective over the default process group (initialised by the caller; world size 1 works without one)."""
+def run(points=1_000_000, keyframes=48, voxel=0.05, parity=True, force_world1=False):
+    """Collective over the default process group (initialised by the caller; world size 1 works without one).
+    force_world1: run the one-rank configuration on THIS GPU only (the N = 1 baseline inside a multi-rank launch)."""
     from util import GOLD, MAPPING, ns
     dfb = importlib.import_module("nerf-fusion_b200")
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() and not force_world1 else 1
+    rank = dist.get_rank() if dist.is_initialized() and not force_world1 else 0
     dev = f"cuda:{torch.cuda.current_device()}"
     W = dfb.weights.load_npz(GOLD / "weights.npz")
     sh = dfb.sharded
@@ -84,10 +85,10 @@ def run(points=1_000_000, keyframes=32, voxel=0.05, parity=True):
     # ---- throughput: config 5
     cfg = dict(MAPPING); cfg.update(bound_min=[-20.0, -2.0, -20.0], bound_max=[20.0, 8.0, 20.0], voxel_size=voxel)
     per_rank = points // world
-    big = make(ns(cfg), per_rank, int(1.25 * 4_400_000 / world) + (1 << 16))
+    big = make(ns(cfg), per_rank, int(1.4 * 100_000 * (keyframes + 2) / world) + (1 << 16))
     m = the_map(big)
-    # 4 x 4 patches of 9 x 9 m on two storeys (y0 = 1.0 / 4.5): 32 keyframes allocate ~4 M voxels
-    tiles = [(-19.0 + 9.5 * (k % 4), -19.0 + 9.5 * (k // 4 % 4), 1.0 + 3.5 * (k // 16 % 2)) for k in range(keyframes + 2)]
+    # 4 x 4 patches of 9 x 9 m on three storeys (y0 = -0.5 / 2.75 / 6.0): 48 keyframes allocate > 4 M voxels
+    tiles = [(-19.0 + 9.5 * (k % 4), -19.0 + 9.5 * (k // 4 % 4), -0.5 + 3.25 * (k // 16 % 3)) for k in range(keyframes + 2)]
     total_ms, total_bytes, total_samples = 0.0, 0, 0
     for k, (x0, z0, y0) in enumerate(tiles):
         P, N = scene_points(per_rank, 100 + 17 * k + rank, (x0, z0), (x0 + 9.0, z0 + 9.0), dev, y0)
@@ -118,7 +119,7 @@ def run(points=1_000_000, keyframes=32, voxel=0.05, parity=True):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=1_000_000)
-    ap.add_argument("--keyframes", type=int, default=32)
+    ap.add_argument("--keyframes", type=int, default=48)
     ap.add_argument("--voxel", type=float, default=0.05)
     a = ap.parse_args()
     world, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

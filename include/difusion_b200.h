@@ -258,6 +258,16 @@ int dfb_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
                        int B, int r, float max_std, int max_tri, float* tri, int64_t* flat_id, float* tri_std,
                        int32_t* d_n_tri, void* stream);
 
+/* One Adam iteration of the latent optimiser, OptimizeProcess.do_optimize (map.py:81-113; disabled by the target config,
+ * do_optimize = False): decoder forward + reverse pass w.r.t. the 29 latent inputs of every sample, Gaussian negative
+ * log-likelihood of the clamped targets (map.py:88-96) averaged over n_samples, gradient scatter-added per latent row, then
+ * torch.optim.Adam's update (lr, betas 0.9 / 0.999, eps 1e-8; `step` is 1-based) with the code regulariser's gradient
+ * reg_scale * x / ||x|| (reg_scale = code_reg_lambda * chunks / n_samples, 0 = off).  latents (n_rows,29) is updated in place;
+ * grad / adam_m / adam_v are (n_rows,29) buffers, zero before the first step (grad is left zero).  FP32 CUDA-core engine. */
+int dfb_latent_adam_step(float* latents, int n_rows, const int64_t* inv, const float* rel_xyz, const float* gt_sdf, int n_samples,
+                         const float* decoder_blob, float* grad, float* adam_m, float* adam_v, int step, float lr, float reg_scale,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sharded map (BASELINE config 5; new functionality, the reference has no multi-GPU map).
  * integrate_keyframe of system/map.py:341-453 over the union of all ranks' points, voxel ids partitioned in 8^3 bricks dealt

@@ -104,6 +104,7 @@ SIGNATURES = {
     "dfb_decode_cubes_ws_bytes": (_SZ, [_I, _I]),
     "dfb_decode_cubes": (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _SZ, _P]),
     "dfb_marching_cubes": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "dfb_latent_adam_step": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _F, _F, _P]),
     "dfb_shard_counter_ints": (_I, []),
     "dfb_shard_local_cells": (_I64, [_I, _I, _I, _I]),
     "dfb_shard_phase1": (_I, [C.POINTER(Shard), _P, _P, _I, _P]),
@@ -124,7 +125,7 @@ KERNELS_PER_CALL = {
     "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
     "gn_kernel": 1,                    # launched inside dfb_gauss_newton (count reported through h_stats[7])
-    "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4,
+    "dfb_latent_adam_step": 2, "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4,
 }
 CALLS = {}
 

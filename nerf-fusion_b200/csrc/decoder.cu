@@ -140,6 +140,73 @@ __global__ void __launch_bounds__(DEC_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
   block_reduce_atomic<29, DEC_T>(acc, packed);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// latent optimiser (map.py:29-113 OptimizeProcess.do_optimize): one Adam iteration = latent_grad_kernel + latent_adam_kernel
+// ------------------------------------------------------------------------------------------------
+// Sample i: latent row inv[i] of `latents`, relative position xyz[i], target gt[i].  Loss (map.py:88-103): negative Gaussian
+// log-likelihood of clamp(gt, +-0.2) under N(clamp(sdf, +-0.2), std), summed and divided by the sample count; its gradient
+// w.r.t. the 29 latent inputs is scatter-added into grad[inv[i]].
+__global__ void __launch_bounds__(DEC_T, 1) latent_grad_kernel(const float* __restrict__ latents, const int64_t* __restrict__ inv,
+                                                               const float* __restrict__ xyz, const float* __restrict__ gt, int n,
+                                                               const float* __restrict__ blob, float inv_n, float* __restrict__ grad) {
+  DecSmem& S = *reinterpret_cast<DecSmem*>(dec_smem_raw);
+  decoder_load_small(S, blob);
+  const int tid = threadIdx.x;
+  for (int base = blockIdx.x * DEC_T; base < n; base += gridDim.x * DEC_T) {
+    const int i = base + tid;
+    const bool valid = i < n;
+    const long long row = valid ? inv[i] : 0;
+    float rel[3] = {0.f, 0.f, 0.f};
+    if (valid) { rel[0] = xyz[3 * (size_t)i]; rel[1] = xyz[3 * (size_t)i + 1]; rel[2] = xyz[3 * (size_t)i + 2]; }
+    load_query(S, latents + row * DFB_LATENT_DIM, rel, valid);
+    float z, u;
+    decoder_forward_tile(S, blob, z, u);
+    const float s = tanhf(z), sd = 0.05f + 0.5f * softplus_torch(u);
+    float seed_z = 0.f, seed_u = 0.f;
+    if (valid) {
+      const float g = fminf(fmaxf(gt[i], -0.2f), 0.2f), pd = fminf(fmaxf(s, -0.2f), 0.2f);
+      const float d = g - pd;
+      // -log N(g; pd, sd) = d^2 / (2 sd^2) + log sd + const
+      const float dl_dpd = (s >= -0.2f && s <= 0.2f) ? -d / (sd * sd) * inv_n : 0.f;        // clamp passes the gradient inside [min, max]
+      const float dl_dsd = (-d * d / (sd * sd * sd) + 1.0f / sd) * inv_n;
+      seed_z = dl_dpd * (1.0f - s * s);
+      seed_u = dl_dsd * 0.5f * softplus_grad(u);
+    }
+    float g_in[DEC_IN];
+    decoder_backward_inputs_tile(S, blob, seed_z, seed_u, g_in);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < DFB_LATENT_DIM; ++k) atomicAdd(grad + row * DFB_LATENT_DIM + k, g_in[k]);
+    }
+  }
+}
+
+// torch.optim.Adam (single tensor, no weight decay, amsgrad off) on (n_rows, 29) latents, one warp per row; adds the code
+// regulariser's gradient reg_scale * x / ||x|| (map.py:98-101) and clears grad for the next iteration.
+__global__ void __launch_bounds__(256) latent_adam_kernel(float* __restrict__ latents, float* __restrict__ grad, float* __restrict__ m1,
+                                                          float* __restrict__ m2, int n_rows, float reg_scale, float beta1, float beta2,
+                                                          float step_size, float bc2_sqrt, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  const size_t i = (size_t)row * DFB_LATENT_DIM + lane;
+  const bool on = lane < DFB_LATENT_DIM;
+  const float x = on ? latents[i] : 0.f;
+  float g = on ? grad[i] : 0.f;
+  if (reg_scale != 0.f) {
+    const float nrm = sqrtf(warp_sum(x * x));
+    if (nrm > 0.f) g += reg_scale * x / nrm;
+  }
+  if (on) {
+    const float m = m1[i] + (1.0f - beta1) * (g - m1[i]);                 // exp_avg.lerp_(grad, 1 - beta1)
+    const float v = m2[i] * beta2 + (1.0f - beta2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    m1[i] = m; m2[i] = v;
+    latents[i] = x - step_size * (m / (sqrtf(v) / bc2_sqrt + eps));      // param.addcdiv_(exp_avg, denom, value = -step_size)
+    grad[i] = 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // decode_cubes
 // ------------------------------------------------------------------------------------------------
@@ -303,6 +370,26 @@ int dfb_get_sdf(const dfb_map_params* h_params, const float* xyz, int n, const i
   get_sdf_kernel<<<dec_grid(n), DEC_T, sizeof(DecSmem), (cudaStream_t)stream>>>(to_dev(h_params), xyz, n, indexer, latent_vecs,
                                                                                 voxel_obs_count, decoder_blob, sdf, std_, valid,
                                                                                 g_sdf, g_std, grad_xyz);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+
+int dfb_latent_adam_step(float* latents, int n_rows, const int64_t* inv, const float* rel_xyz, const float* gt_sdf, int n_samples,
+                         const float* decoder_blob, float* grad, float* adam_m, float* adam_v, int step, float lr, float reg_scale,
+                         void* stream) {
+  DFB_CHECK_ARG(n_rows >= 0 && n_samples >= 0 && step >= 1, "latent_adam_step");
+  if (n_rows == 0 || n_samples == 0) return DFB_OK;
+  DFB_CHECK_ARG(latents && inv && rel_xyz && gt_sdf && decoder_blob && grad && adam_m && adam_v, "latent_adam_step: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = set_dec_smem(latent_grad_kernel);
+  if (rc) return rc;
+  latent_grad_kernel<<<dec_grid(n_samples), DEC_T, sizeof(DecSmem), s>>>(latents, inv, rel_xyz, gt_sdf, n_samples, decoder_blob,
+                                                                        1.0f / (float)n_samples, grad);
+  const double b1 = 0.9, b2 = 0.999;                       // torch.optim.Adam defaults (map.py:84)
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  latent_adam_kernel<<<div_up((long long)n_rows * 32, 256), 256, 0, s>>>(latents, grad, adam_m, adam_v, n_rows, reg_scale, (float)b1, (float)b2,
+                                                                        (float)(lr / bc1), (float)sqrt(bc2), 1e-8f);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -154,6 +154,38 @@ __device__ __forceinline__ void decoder_backward_tile(DecSmem& S, const float* _
   g[0] = gx; g[1] = gy; g[2] = gz;
 }
 
+
+// Reverse pass with the gradient w.r.t. ALL 32 network inputs (29 latent + 3 xyz), for the latent optimiser
+// (map.py:81-113 back-propagates into latent_vecs_unique): g_in[k] = sum_o delta0[o] W0[o][k] + sum_o delta3[o] W3[o][96 + k].
+// The two products read the forward operands transposed (F0 / F3 are [k][o] in chunks of 64 outputs); warp-uniform
+// addresses, i.e. broadcast loads.  Not a hot path (the optimiser is disabled by the target config).
+__device__ __forceinline__ void decoder_backward_inputs_tile(DecSmem& S, const float* __restrict__ blob, float seed_z, float seed_u,
+                                                             float g_in[DEC_IN]) {
+  const float* sm = S.small_;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < DEC_IN; ++k) g_in[k] = 0.f;
+#pragma unroll 1
+  for (int o = 0; o < 128; ++o) {                 // delta3 = (seed_z W4 + seed_u Wu) * [a3 > 0]  -> actA
+    const uint32_t bit = (S.masks[(3 * 4 + (o >> 5)) * DEC_T + tid] >> (o & 31)) & 1u;
+    const float d = bit ? fmaf(seed_z, sm[DS_W4 + o], seed_u * sm[DS_WU + o]) : 0.f;
+    S.actA[o * DEC_T + tid] = d;
+    const float* w = blob + DB_F3 + (o >> 6) * (128 * 64) + (o & 63);       // F3[(96 + k)][o]
+#pragma unroll
+    for (int k = 0; k < DEC_IN; ++k) g_in[k] = fmaf(__ldg(w + (96 + k) * 64), d, g_in[k]);
+  }
+  dense<false>(S, S.actA, 128, nullptr, 0, blob + DB_B3, nullptr, 96, S.actB, 2);    // delta2
+  dense<false>(S, S.actB, 96, nullptr, 0, blob + DB_B2, nullptr, 128, S.actA, 1);    // delta1
+  dense<false>(S, S.actA, 128, nullptr, 0, blob + DB_B1, nullptr, 128, S.actB, 0);   // delta0
+#pragma unroll 1
+  for (int o = 0; o < 128; ++o) {
+    const float d = S.actB[o * DEC_T + tid];
+    const float* w = blob + DB_F0 + (o >> 6) * (32 * 64) + (o & 63);        // F0[k][o]
+#pragma unroll
+    for (int k = 0; k < DEC_IN; ++k) g_in[k] = fmaf(__ldg(w + k * 64), d, g_in[k]);
+  }
+}
+
 __device__ __forceinline__ void decoder_load_small(DecSmem& S, const float* __restrict__ blob) {
   for (int t = threadIdx.x; t < DS_SIZE; t += DEC_T) S.small_[t] = __ldg(blob + DB_SMALL + t);
   __syncthreads();

@@ -59,6 +59,13 @@ class SimpleMesh:
         self.vertex_std = vertex_std
 
 
+class SimpleLineSet:
+    """Stand-in for open3d.geometry.LineSet when open3d is not installed."""
+
+    def __init__(self, points, lines, colors=None):
+        self.points, self.lines, self.colors = points, lines, colors
+
+
 class _GetSdfFn(torch.autograd.Function):
     """sdf/std of every query row with the reverse pass done by the same kernel (replaces the autograd tape the
     reference builds through forward_model(no_detach=True), map.py:578-579)."""
@@ -91,7 +98,8 @@ class DenseIndexedMap:
         in cold_vars are views of the first `capacity` rows, and capacity still doubles from 1 like map.py:263-285, so
         growing the map is a re-slice -- no allocation or copy in the frame loop until the reservation is exceeded."""
         if enable_async:
-            raise NotImplementedError("async optimisation/meshing is out of scope (run_async: false, SURVEY.md §8 I7)")
+            raise NotImplementedError("the asynchronous optimisation process / meshing thread are not provided (run_async: false); "
+                                      "the optimiser itself runs synchronously (integrate_keyframe(do_optimize=True))")
         if latent_dim != 29:
             raise ValueError("kernels are specialised for the shipped checkpoint (latent dim 29, hyper.json)")
         self.device = torch.device(device)
@@ -247,8 +255,9 @@ class DenseIndexedMap:
         """map.py:341-520 with do_optimize=False.  Returns unq_mask (N,) bool (None when prune_min_vox_obs <= 0)."""
         assert surface_xyz.device == surface_normal.device == self.device, \
             f"Device of map {self.device} and input observation {surface_xyz.device, surface_normal.device} must be the same."
-        if do_optimize:
-            raise NotImplementedError("latent optimisation (map.py:460-517) is out of scope; main.py calls do_optimize=False")
+        if async_optimize and do_optimize:
+            raise NotImplementedError("asynchronous latent optimisation (a second process, map.py:29-79) is not provided; "
+                                      "do_optimize=True runs synchronously like the reference's async_optimize=False")
         xyz = surface_xyz.detach().contiguous().float()
         nrm = surface_normal.detach().contiguous().float()
         n = xyz.size(0)
@@ -270,7 +279,72 @@ class DenseIndexedMap:
                                            ws.numel(), st))
         self.n_occupied = self.n_occupied + n_new
         self.last_integrate_stats = self._stats
+        if do_optimize and getattr(self.args, "optim_n_iters", 0) > 0:
+            self._optimize_latents(xyz, nrm, mask if self.args.prune_min_vox_obs > 0 else None)
         return mask if self.args.prune_min_vox_obs > 0 else None
+
+    def _optimize_latents(self, xyz, nrm, unq_mask):
+        """map.py:456-517 with async_optimize=False: voxels whose confidence reached encoder_count_th and that were not optimised
+        yet get their latents refined by `optim_n_iters` Adam steps on perturbed surface samples (do_optimize, map.py:81-113).
+        The sample gathering is the reference's torch code line for line (so that, with the same torch seed, the random
+        offsets along the normals are the same numbers); decoder forward / reverse pass and Adam are dfb_latent_adam_step."""
+        args = self.args
+        n_occ = self.n_occupied
+        sel = torch.logical_and(self.voxel_obs_count[:n_occ] >= args.encoder_count_th, ~self.voxel_optimized[:n_occ])
+        optim_voxel_pos = self.latent_vecs_pos[:n_occ][sel]
+        optim_voxel_pos = optim_voxel_pos[optim_voxel_pos > 0]                  # (sic: map.py:467 drops voxel id 0)
+        if optim_voxel_pos.size(0) == 0:
+            return
+        vs = self.voxel_size
+        zeroed = xyz - self.bound_min.unsqueeze(0)
+        # tensor / tensor is an IEEE divide on CUDA, tensor / python-float multiplies by the reciprocal (what the reference executes)
+        xn = zeroed / torch.tensor(vs, dtype=torch.float32, device=self.device) if self.div_mode == DIV_IEEE else zeroed / vs
+        gid = self._linearize_id(torch.ceil(xn).long() - 1)
+        if unq_mask is not None:
+            xn, gid, nrm = xn[unq_mask], gid[unq_mask], nrm[unq_mask]
+        map_status = torch.zeros((self.n_cells,), device=self.device, dtype=torch.short)
+        map_status[optim_voxel_pos] |= 1
+        exp_indexer = torch.zeros((self.n_cells,), device=self.device, dtype=torch.long)
+        exp_indexer[self._expand_flatten_id(optim_voxel_pos, False)] = 1
+        focus = exp_indexer[gid] == 1
+        pxn, pn = xn[focus], nrm[focus]
+        inds, rels, sdfs = [], [], []
+        n_xyz = self.n_xyz
+        for off in ([-0.5, -0.5, -0.5], [-0.5, -0.5, 0.5], [-0.5, 0.5, -0.5], [-0.5, 0.5, 0.5],
+                    [0.5, -0.5, -0.5], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5], [0.5, 0.5, 0.5]):
+            g = torch.ceil(pxn + torch.tensor(off, device=self.device, dtype=torch.float32)) - 1
+            for dim in range(3):
+                g[:, dim].clamp_(0, n_xyz[dim] - 1)
+            rel = pxn - g - 0.5
+            lin = self._linearize_id(g.long())
+            ok = map_status[lin] >= 1
+            cur_rel, cur_n = rel[ok], pn[ok]
+            cur_sdf = torch.randn(cur_rel.size(0), device=self.device, dtype=torch.float32) * 0.05
+            inds.append(self.indexer[lin][ok]); rels.append(cur_rel + cur_sdf.unsqueeze(-1) * cur_n); sdfs.append(cur_sdf)
+        inds, rels, sdfs = torch.cat(inds), torch.cat(rels).contiguous(), torch.cat(sdfs).contiguous()
+        if inds.numel() == 0:
+            return
+        uniq, inv = torch.unique(inds, return_inverse=True)
+        lat = self.latent_vecs[uniq].contiguous()
+        self.latent_vecs[uniq] = self.optimize_latents(lat, inv.contiguous(), sdfs, rels)
+        self._updated_flag[uniq] = 1                                           # _mark_updated_vec_id (map.py:336)
+        self.voxel_optimized[uniq] = True
+
+    def optimize_latents(self, latent_vecs_unique, latent_id_inv_mapping, gathered_sdf, gathered_relative_xyz):
+        """OptimizeProcess.do_optimize (map.py:81-113): Adam(lr 1e-2) for args.optim_n_iters iterations on the Gaussian
+        log-likelihood of the clamped SDF targets (+ the optional code regulariser); returns the optimised latents."""
+        args = self.args
+        lat = latent_vecs_unique.detach().clone().contiguous().float()
+        n_rows, n = lat.size(0), int(latent_id_inv_mapping.size(0))
+        grad, m1, m2 = torch.zeros_like(lat), torch.zeros_like(lat), torch.zeros_like(lat)
+        chunks = max(1, -(-n // int(1.5e6)))                                   # forward_model's max_sample: the regulariser is added per chunk
+        reg = float(args.code_reg_lambda) * chunks / n if getattr(args, "code_regularization", False) else 0.0
+        inv = latent_id_inv_mapping.contiguous().long(); xyz = gathered_relative_xyz.contiguous().float(); gt = gathered_sdf.contiguous().float()
+        with torch.cuda.device(self.device):
+            for it in range(int(args.optim_n_iters)):
+                check(self.lib.dfb_latent_adam_step(_p(lat), n_rows, _p(inv), _p(xyz), _p(gt), n, _p(self.decoder_blob), _p(grad), _p(m1),
+                                                    _p(m2), it + 1, 1.0e-2, reg, _stream()))
+        return lat
 
     # ------------------------------------------------------------------------------------------ query
     def _get_sdf_raw(self, xyz, g_sdf, g_std):
@@ -372,6 +446,34 @@ class DenseIndexedMap:
             mc.vertices_flatten_id = np.concatenate([mc.vertices_flatten_id[keep], vertices_flatten_id], axis=0)
             mc.vertices_std = np.concatenate([mc.vertices_std[keep], vertices_std], axis=0)
         return self._make_mesh_from_cache()
+
+    def get_fast_preview_visuals(self):
+        """map.py:726-750 (the GUI's block wireframe, main.py:89 under --vis): one cube outline per allocated voxel + the map's
+        bounding box.  Returns [blocks, bbox]: open3d LineSets when open3d is installed, else SimpleLineSet(points, lines, colors)."""
+        occupied = torch.where(self.indexer != -1)[0]
+        base = self._unlinearize_id(occupied).float() * self.voxel_size + self.bound_min
+        vs = self.voxel_size
+        offs = [[0.0, 0.0, 0.0], [0.0, 0.0, vs], [0.0, vs, 0.0], [0.0, vs, vs], [vs, 0.0, 0.0], [vs, 0.0, vs], [vs, vs, 0.0], [vs, vs, vs]]
+        verts = torch.cat([base + torch.tensor(o, dtype=torch.float32, device=base.device).unsqueeze(0) for o in offs], 0)
+        n = base.size(0)
+        ar = np.arange(n, dtype=np.int32)
+        edges = np.concatenate([np.stack([ar + a * n, ar + b * n], 1) for a, b in
+                                ([0, 1], [0, 2], [0, 4], [1, 3], [1, 5], [2, 3], [2, 6], [3, 7], [4, 5], [4, 6], [5, 7], [6, 7])], 0)
+        verts = verts.cpu().numpy().astype(float)
+        lo, hi = self.bound_min.cpu().numpy().astype(float), self.bound_max.cpu().numpy().astype(float)
+        bb_pts = np.asarray([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+        bb_lines = np.asarray([[0, 1], [2, 3], [4, 5], [6, 7], [0, 4], [1, 5], [2, 6], [3, 7], [0, 2], [4, 6], [1, 3], [5, 7]], np.int32)
+        bb_col = np.repeat(np.asarray([[0.5804, 0.4039, 0.7412]]), 12, 0)          # matplotlib tab10[4] (vis_util.py:120, color_id=4)
+        try:
+            import open3d as o3d
+            if not hasattr(o3d.geometry, "LineSet"):
+                raise ImportError("open3d.geometry.LineSet")
+            blk = o3d.geometry.LineSet(points=o3d.utility.Vector3dVector(verts), lines=o3d.utility.Vector2iVector(edges))
+            bb = o3d.geometry.LineSet(points=o3d.utility.Vector3dVector(bb_pts), lines=o3d.utility.Vector2iVector(bb_lines))
+            bb.colors = o3d.utility.Vector3dVector(bb_col)
+            return [blk, bb]
+        except ImportError:
+            return [SimpleLineSet(verts, edges, None), SimpleLineSet(bb_pts, bb_lines, bb_col)]
 
     def _make_mesh_from_cache(self):
         """map.py:522-544."""

@@ -91,7 +91,7 @@ def run_reference(frames, calib, device, iter_config=None, integrate_interval=20
     return out
 
 
-def make_ours(device, iter_config=None, div_mode=1):
+def make_ours(device, iter_config=None, div_mode=1, mapping_over=None):
     """div_mode 1 (DFB_DIV_RECIP): torch CUDA divides by a Python scalar as a reciprocal multiply, which is what the
     reference executes on the GPU; 0 (DFB_DIV_IEEE) reproduces torch CPU."""
     import argparse
@@ -110,6 +110,8 @@ def make_ours(device, iter_config=None, div_mode=1):
         mapping, tracking = dict(MAPPING), dict(TRACKING)
     if iter_config is not None:
         tracking = dict(tracking); tracking["iter_config"] = iter_config
+    if mapping_over:
+        mapping = dict(mapping); mapping.update(mapping_over)
 
     def ns(d):
         a = argparse.Namespace(); a.__dict__.update(d); return a

@@ -149,14 +149,17 @@ def load_config():
     return yaml.safe_load((ref_root() / "configs" / "fusion-lr-kt.yaml").read_text())
 
 
-def make_reference_system(device, iter_config=None):
+def make_reference_system(device, iter_config=None, mapping_over=None):
     """(map, tracker, cfg) exactly as main.py:112-133 builds them (configs/fusion-lr-kt.yaml, ckpt/default, epoch 300)."""
     ref = install(_BACKEND["name"] or "reference")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     model, margs = load_reference_model(device)
     cfg = load_config()
-    m = ref.map.DenseIndexedMap(model, ref.exp.dict_to_args(cfg["mapping"]), margs.code_length, torch.device(device), False, None)
+    mapping = dict(cfg["mapping"])
+    if mapping_over:
+        mapping.update(mapping_over)
+    m = ref.map.DenseIndexedMap(model, ref.exp.dict_to_args(mapping), margs.code_length, torch.device(device), False, None)
     targs = ref.exp.dict_to_args(cfg["tracking"])
     if iter_config is not None:
         targs.iter_config = iter_config

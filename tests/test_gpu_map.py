@@ -201,6 +201,19 @@ def test_full_frame_integrate_vs_oracle(weights):
         assert m2.n_occupied == m.n_occupied and torch.equal(m2.indexer, m.indexer)
 
 
+def test_fast_preview_visuals(gmap):
+    """map.py:726-750: one cube outline (8 vertices, 12 edges) per allocated voxel, corner 0 at the voxel's minimum corner."""
+    blk, bb = gmap.get_fast_preview_visuals()
+    n = gmap.n_occupied
+    pts, lines = np.asarray(blk.points), np.asarray(blk.lines)
+    assert pts.shape == (8 * n, 3) and lines.shape == (12 * n, 2) and np.asarray(bb.points).shape == (8, 3)
+    pos = gmap._unlinearize_id(torch.where(gmap.indexer != -1)[0]).float() * gmap.voxel_size + gmap.bound_min
+    assert np.allclose(pts[:n], pos.cpu().numpy())
+    assert np.allclose(pts[7 * n:] - pts[:n], gmap.voxel_size)            # corner 7 = + (vs, vs, vs)
+    d = np.abs(pts[lines[:, 0]] - pts[lines[:, 1]])
+    assert np.allclose(d.sum(1), gmap.voxel_size) and np.allclose(d.max(1), gmap.voxel_size)   # every edge is axis-aligned, one voxel long
+
+
 def test_integrate_edge_cases(weights):
     m = make_map(weights)
     empty = torch.zeros((0, 3), device=DEV)

@@ -226,3 +226,49 @@ def test_transform_points_equals_torch():
     rot = (iso.rotation @ x).cpu().numpy()
     assert np.abs(rot - (x.cpu() @ R.cpu().t()).numpy()).max() <= 4e-7 * 6
     assert (iso @ x[:0]).shape == (0, 3)
+
+
+def test_latent_adam_step_vs_torch(weights):
+    """dfb_latent_adam_step (latent optimiser, map.py:81-113): gradient of the Gaussian log-likelihood w.r.t. the 29 latent inputs
+    + torch.optim.Adam's update, against torch autograd on the oracle networks (CPU) with the same loss and regulariser."""
+    from util import make_map
+    d = pkg()
+    m = make_map(weights)
+    torch.manual_seed(0)
+    U, n = 50, 4000
+    lat = torch.randn(U, 29) * 0.1
+    inv = torch.randint(0, U, (n,))
+    xyz = torch.rand(n, 3) - 0.5
+    gt = torch.randn(n) * 0.05
+    lam = 1e-4
+
+    def torch_run(iters):
+        x = lat.clone().requires_grad_(True)
+        opt = torch.optim.Adam([x], lr=1e-2)
+        g1 = None
+        for _ in range(iters):
+            opt.zero_grad()
+            s, sd = nets.decoder_forward(weights, torch.cat([x[inv], xyz], 1))
+            ll = -torch.distributions.Normal(loc=torch.clamp(s.squeeze(-1), -0.2, 0.2), scale=sd.squeeze(-1)).log_prob(torch.clamp(gt, -0.2, 0.2))
+            (ll.sum() / n + lam * torch.sum(torch.norm(x, dim=1)) / n).backward()
+            g1 = x.grad.clone() if g1 is None else g1
+            opt.step()
+        return x.detach(), g1
+    m.args.code_regularization = True; m.args.code_reg_lambda = lam
+    # one step is exact to rounding; later steps divide by sqrt(v) of gradients around 1e-6, which amplifies last-bit differences
+    for iters, tol in ((1, 1e-6), (3, 5e-3)):
+        ref, g1 = torch_run(iters)
+        m.args.optim_n_iters = iters
+        out = m.optimize_latents(lat.to(DEV), inv.to(DEV), gt.to(DEV), xyz.to(DEV)).cpu()
+        err = (out - ref).abs().max().item()
+        print(f"{iters} Adam step(s): max |ours - torch| {err:.2e}, moved {(out - lat).abs().max().item():.3e}")
+        assert err < tol
+    # the gradient itself: first moment after one step with lr = 0 is 0.1 * grad
+    lat_d, inv_d, xyz_d, gt_d = lat.to(DEV).contiguous(), inv.to(DEV), xyz.to(DEV).contiguous(), gt.to(DEV)
+    grad, m1, m2 = torch.zeros_like(lat_d), torch.zeros_like(lat_d), torch.zeros_like(lat_d)
+    p = d.ext._p
+    d._lib.check(m.lib.dfb_latent_adam_step(p(lat_d), U, p(inv_d), p(xyz_d), p(gt_d), n, p(m.decoder_blob), p(grad), p(m1), p(m2), 1, 0.0,
+                                            lam / n, d.ext._stream()))
+    g = (m1 / 0.1).cpu()
+    assert (g - g1).abs().max() <= 1e-5 * g1.abs().max()
+    assert float(grad.abs().sum()) == 0.0                          # left zero for the next iteration

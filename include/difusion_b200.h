@@ -310,6 +310,8 @@ typedef struct {
   void* peer_ids[DFB_SHARD_MAX_WORLD]; int32_t* peer_ids_count[DFB_SHARD_MAX_WORLD];
   void* peer_smp[DFB_SHARD_MAX_WORLD]; int32_t* peer_smp_count[DFB_SHARD_MAX_WORLD];
   void* peer_dlt[DFB_SHARD_MAX_WORLD]; int32_t* peer_dlt_count[DFB_SHARD_MAX_WORLD];
+  /* barrier flags: `flags` = this rank's `world` epoch slots (slot s written by rank s), peer_flags[d] = this rank's slot at rank d */
+  int32_t* flags; int32_t* peer_flags[DFB_SHARD_MAX_WORLD];
 } dfb_shard;
 
 int dfb_shard_counter_ints(void);
@@ -326,6 +328,12 @@ int dfb_shard_phase4(const dfb_shard* S, void* stream);
  * {points received, samples received, voxels allocated, error bits, n_occupied, voxels updated, -, -, points sent to rank d..,
  * samples sent to rank d..}. */
 int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_stats, void* stream);
+
+/* Barrier between two phases, as a kernel: every rank stores `epoch` (monotonically increasing, > 0) into its slot of every
+ * peer's flag array (peer stores, after a system-scope fence that orders the phase's record stores before it) and waits until all
+ * of its own slots have reached `epoch`.  Each rank runs this on its OWN GPU, so the waits cannot starve one another; the wait is
+ * bounded (~2 s) and traps instead of hanging.  An alternative to a 4-byte NCCL all-reduce (a few microseconds instead of ~20). */
+int dfb_shard_barrier(const dfb_shard* S, int epoch, void* stream);
 
 /* Peer-mappable device memory (cudaMalloc + CUDA IPC): alloc returns the pointer and a 64-byte handle another process on the
  * same node opens with dfb_peer_open (peer access over NVLink is enabled lazily by the driver). */

@@ -54,7 +54,8 @@ class Shard(C.Structure):
                 ("peer_pts", C.c_void_p * SHARD_MAX_WORLD), ("peer_pts_count", C.c_void_p * SHARD_MAX_WORLD),
                 ("peer_ids", C.c_void_p * SHARD_MAX_WORLD), ("peer_ids_count", C.c_void_p * SHARD_MAX_WORLD),
                 ("peer_smp", C.c_void_p * SHARD_MAX_WORLD), ("peer_smp_count", C.c_void_p * SHARD_MAX_WORLD),
-                ("peer_dlt", C.c_void_p * SHARD_MAX_WORLD), ("peer_dlt_count", C.c_void_p * SHARD_MAX_WORLD)]
+                ("peer_dlt", C.c_void_p * SHARD_MAX_WORLD), ("peer_dlt_count", C.c_void_p * SHARD_MAX_WORLD),
+                ("flags", C.c_void_p), ("peer_flags", C.c_void_p * SHARD_MAX_WORLD)]
 
 
 _P = C.c_void_p
@@ -112,6 +113,7 @@ SIGNATURES = {
     "dfb_shard_phase3": (_I, [C.POINTER(Shard), _P]),
     "dfb_shard_phase4": (_I, [C.POINTER(Shard), _P]),
     "dfb_shard_phase5": (_I, [C.POINTER(Shard), _P, _P, _P]),
+    "dfb_shard_barrier": (_I, [C.POINTER(Shard), _I, _P]),
     "dfb_peer_alloc": (_I, [_SZ, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
     "dfb_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "dfb_peer_close": (_I, [_P]),
@@ -125,7 +127,7 @@ KERNELS_PER_CALL = {
     "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
     "gn_kernel": 1,                    # launched inside dfb_gauss_newton (count reported through h_stats[7])
-    "dfb_latent_adam_step": 2, "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4,
+    "dfb_latent_adam_step": 2, "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4, "dfb_shard_barrier": 1,
 }
 CALLS = {}
 

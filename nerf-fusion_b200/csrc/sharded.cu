@@ -364,6 +364,22 @@ __global__ void rearm_kernel(int* __restrict__ counters, int* __restrict__ delta
   }
 }
 
+struct FlagPtrs { int* p[MAXW]; };
+__global__ void peer_barrier_kernel(FlagPtrs peers, volatile int* mine, int world, int epoch) {
+  const int d = threadIdx.x;
+  if (d < world) {
+    __threadfence_system();                       // this rank's earlier peer stores are ordered before the flag
+    *reinterpret_cast<volatile int*>(peers.p[d]) = epoch;
+    __threadfence_system();
+    const long long t0 = clock64();
+    while (mine[d] < epoch) {
+      __nanosleep(200);
+      if (clock64() - t0 > 4000000000LL) __trap();              // ~2 s: a peer is gone; fail loudly instead of hanging
+    }
+  }
+  __threadfence_system();
+}
+
 static Channel channel(void* const* peers, int cap, int world) {
   Channel c;
   for (int d = 0; d < MAXW; ++d) c.dst[d] = d < world ? peers[d] : nullptr;
@@ -461,6 +477,16 @@ int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_s
   finalize_kernel<<<2 * sm_count(), 256, 0, s>>>(g, S->counters, S->touched, S->acc, S->acc_n, S->latent_vecs, S->voxel_obs_count, S->latent_vecs_pos,
                                                S->next_delta, S->n_next_delta, S->delta_cap);
   rearm_kernel<<<1, 256, 0, s>>>(S->counters, S->delta_list, S->next_delta, S->n_next_delta, S->delta_cap, d_stats);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_shard_barrier(const dfb_shard* S, int epoch, void* stream) {
+  SHARD_CHECK(S);
+  DFB_CHECK_ARG(S->flags && epoch > 0, "shard_barrier");
+  FlagPtrs fp;
+  for (int d = 0; d < MAXW; ++d) fp.p[d] = d < S->world ? S->peer_flags[d] : nullptr;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fp, S->flags, S->world, epoch);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

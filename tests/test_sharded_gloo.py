@@ -66,7 +66,7 @@ def _fabric_worker(rank, world, port, out_dir):
     sh = importlib.import_module("nerf-fusion_b200.sharded")
     # a stand-in for one rank's memory: only what the handle exchange and the table construction look at
     mem = types.SimpleNamespace(inbox_ptr=0x10000000 * (rank + 1), handle=bytes([rank]) * 64,
-                                off={"pts": 0, "smp": 4096, "ids": 8192, "dlt": 12288, "cnt": 16384}, pts_cap=16, smp_cap=32, ids_cap=8, dlt_cap=8)
+                                off={"pts": 0, "smp": 4096, "ids": 8192, "dlt": 12288, "cnt": 16384, "flg": 16512}, pts_cap=16, smp_cap=32, ids_cap=8, dlt_cap=8)
     mem.cap = lambda ch: getattr(mem, ch + "_cap")
     mem.rec_bytes = lambda ch: 32 if ch in ("pts", "smp") else 4
     handles = [None] * world

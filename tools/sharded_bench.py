@@ -23,7 +23,7 @@ def scene_points(n, seed, lo, hi, dev, y0=1.0):
     return torch.stack([x, y, z], 1).contiguous(), nrm.contiguous()
 
 
-def run(points=1_000_000, keyframes=48, voxel=0.05, parity=True, force_world1=False):
+def run(points=1_000_000, keyframes=48, voxel=0.05, parity=True, force_world1=False, barrier="peer"):
     """Collective over the default process group (initialised by the caller; world size 1 works without one).
     force_world1: run the one-rank configuration on THIS GPU only (the N = 1 baseline inside a multi-rank launch)."""
     from util import GOLD, MAPPING, ns
@@ -37,7 +37,7 @@ def run(points=1_000_000, keyframes=48, voxel=0.05, parity=True, force_world1=Fa
     def make(args, max_pts, capacity):
         if world == 1:
             return sh.LocalFabric.create(W, args, dev, 1, max_pts, capacity)
-        return sh.IpcFabric.create(W, args, dev, max_pts, capacity)
+        return sh.IpcFabric.create(W, args, dev, max_pts, capacity, barrier=barrier)
 
     def integrate(fab, P, N):
         if world == 1:
@@ -122,7 +122,7 @@ def run(points=1_000_000, keyframes=48, voxel=0.05, parity=True, force_world1=Fa
     out = {"workload": "config 5: sharded map, %d keyframes x %d points, voxel %.3f m, %d grid cells" % (keyframes, points, voxel, m.G),
            "n_gpus": world, "points_per_s": keyframes * points / (total_ms * 1e-3), "ms_per_keyframe": total_ms / keyframes,
            "samples_per_keyframe": total_samples / keyframes, "peer_store_bytes_per_keyframe": total_bytes / keyframes,
-           "voxels_total": int(nv.item()), "transport": "peer stores from the producing kernels (CUDA IPC over NVLink), 4 x 4-byte NCCL all-reduce barriers per keyframe, no host sync",
+           "voxels_total": int(nv.item()), "transport": "peer stores from the producing kernels (CUDA IPC over NVLink), 4 barriers per keyframe (%s), no host sync" % ("epoch flags exchanged by peer stores" if barrier == "peer" else "4-byte NCCL all-reduce"),
            "parity_vs_single_gpu": par}
     return out
 
@@ -132,12 +132,13 @@ if __name__ == "__main__":
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--keyframes", type=int, default=48)
     ap.add_argument("--voxel", type=float, default=0.05)
+    ap.add_argument("--barrier", default="peer", choices=["peer", "nccl"])
     a = ap.parse_args()
     world, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    res = run(a.points, a.keyframes, a.voxel)
+    res = run(a.points, a.keyframes, a.voxel, barrier=a.barrier)
     if int(os.environ.get("RANK", 0)) == 0:
         print(json.dumps(res))
     if world > 1:

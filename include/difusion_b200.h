@@ -312,6 +312,7 @@ typedef struct {
   void* peer_dlt[DFB_SHARD_MAX_WORLD]; int32_t* peer_dlt_count[DFB_SHARD_MAX_WORLD];
   /* barrier flags: `flags` = this rank's `world` epoch slots (slot s written by rank s), peer_flags[d] = this rank's slot at rank d */
   int32_t* flags; int32_t* peer_flags[DFB_SHARD_MAX_WORLD];
+  int32_t fuse_publish;        /* 1: the per-pair record counts are published by dfb_shard_barrier (one launch less per phase) */
 } dfb_shard;
 
 int dfb_shard_counter_ints(void);
@@ -331,9 +332,10 @@ int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_s
 
 /* Barrier between two phases, as a kernel: every rank stores `epoch` (monotonically increasing, > 0) into its slot of every
  * peer's flag array (peer stores, after a system-scope fence that orders the phase's record stores before it) and waits until all
- * of its own slots have reached `epoch`.  Each rank runs this on its OWN GPU, so the waits cannot starve one another; the wait is
+ * of its own slots have reached `epoch`.  With S->fuse_publish it first publishes the record counts of the phase that just ran
+ * (`after_phase` = 1, 2 or 4; 3 publishes nothing).  Each rank runs this on its OWN GPU, so the waits cannot starve one another; the wait is
  * bounded (~2 s) and traps instead of hanging.  An alternative to a 4-byte NCCL all-reduce (a few microseconds instead of ~20). */
-int dfb_shard_barrier(const dfb_shard* S, int epoch, void* stream);
+int dfb_shard_barrier(const dfb_shard* S, int epoch, int after_phase, void* stream);
 
 /* Peer-mappable device memory (cudaMalloc + CUDA IPC): alloc returns the pointer and a 64-byte handle another process on the
  * same node opens with dfb_peer_open (peer access over NVLink is enabled lazily by the driver). */

@@ -55,7 +55,7 @@ class Shard(C.Structure):
                 ("peer_ids", C.c_void_p * SHARD_MAX_WORLD), ("peer_ids_count", C.c_void_p * SHARD_MAX_WORLD),
                 ("peer_smp", C.c_void_p * SHARD_MAX_WORLD), ("peer_smp_count", C.c_void_p * SHARD_MAX_WORLD),
                 ("peer_dlt", C.c_void_p * SHARD_MAX_WORLD), ("peer_dlt_count", C.c_void_p * SHARD_MAX_WORLD),
-                ("flags", C.c_void_p), ("peer_flags", C.c_void_p * SHARD_MAX_WORLD)]
+                ("flags", C.c_void_p), ("peer_flags", C.c_void_p * SHARD_MAX_WORLD), ("fuse_publish", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -113,7 +113,7 @@ SIGNATURES = {
     "dfb_shard_phase3": (_I, [C.POINTER(Shard), _P]),
     "dfb_shard_phase4": (_I, [C.POINTER(Shard), _P]),
     "dfb_shard_phase5": (_I, [C.POINTER(Shard), _P, _P, _P]),
-    "dfb_shard_barrier": (_I, [C.POINTER(Shard), _I, _P]),
+    "dfb_shard_barrier": (_I, [C.POINTER(Shard), _I, _I, _P]),
     "dfb_peer_alloc": (_I, [_SZ, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
     "dfb_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "dfb_peer_close": (_I, [_P]),

@@ -365,9 +365,11 @@ __global__ void rearm_kernel(int* __restrict__ counters, int* __restrict__ delta
 }
 
 struct FlagPtrs { int* p[MAXW]; };
-__global__ void peer_barrier_kernel(FlagPtrs peers, volatile int* mine, int world, int epoch) {
+__global__ void peer_barrier_kernel(FlagPtrs peers, volatile int* mine, int world, int epoch, const int* __restrict__ cursors, int cap,
+                                    CountPtrs cp) {
   const int d = threadIdx.x;
   if (d < world) {
+    if (cursors) *cp.p[d] = min(cursors[d], cap);   // the phase's per-pair record counts travel with the barrier
     __threadfence_system();                       // this rank's earlier peer stores are ordered before the flag
     *reinterpret_cast<volatile int*>(peers.p[d]) = epoch;
     __threadfence_system();
@@ -421,7 +423,7 @@ int dfb_shard_phase1(const dfb_shard* S, const float* xyz, const float* normal, 
     DFB_CHECK_ARG(xyz && normal, "shard: null input");
     route_points_kernel<<<div_up(n, 256), 256, 0, s>>>(g, xyz, normal, n, channel(S->peer_pts, S->pts_cap, S->world), S->counters);
   }
-  publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_PTS, S->pts_cap, count_ptrs(S->peer_pts_count, S->world), S->world);
+  if (!S->fuse_publish) publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_PTS, S->pts_cap, count_ptrs(S->peer_pts_count, S->world), S->world);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -435,7 +437,7 @@ int dfb_shard_phase2(const dfb_shard* S, void* stream) {
   prune_alloc_kernel<<<grid, 256, 0, s>>>(g, reinterpret_cast<PointRec*>(S->pts_inbox), S->pts_count, S->pts_cap, S->grid_count, S->indexer_local,
                                           S->latent_vecs_pos, S->capacity, S->counters, S->delta_list, S->delta_cap,
                                           channel(S->peer_ids, S->ids_cap, S->world));
-  publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_IDS, S->ids_cap, count_ptrs(S->peer_ids_count, S->world), S->world);
+  if (!S->fuse_publish) publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_IDS, S->ids_cap, count_ptrs(S->peer_ids_count, S->world), S->world);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -459,7 +461,7 @@ int dfb_shard_phase4(const dfb_shard* S, void* stream) {
   apply_deltas_kernel<<<seg_grid(S->dlt_cap, S->world), 256, 0, s>>>(S->dlt_inbox, S->dlt_count, S->dlt_cap, S->cand_bits);
   emit_samples_kernel<<<seg_grid(S->pts_cap, S->world), 256, 0, s>>>(g, reinterpret_cast<const PointRec*>(S->pts_inbox), S->pts_count, S->pts_cap,
                                                                     S->cand_bits, S->grid_count, S->counters, channel(S->peer_smp, S->smp_cap, S->world));
-  publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_SMP, S->smp_cap, count_ptrs(S->peer_smp_count, S->world), S->world);
+  if (!S->fuse_publish) publish_counts_kernel<<<1, 32, 0, s>>>(S->counters + C_SMP, S->smp_cap, count_ptrs(S->peer_smp_count, S->world), S->world);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -481,12 +483,20 @@ int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_s
   return DFB_OK;
 }
 
-int dfb_shard_barrier(const dfb_shard* S, int epoch, void* stream) {
+int dfb_shard_barrier(const dfb_shard* S, int epoch, int after_phase, void* stream) {
   SHARD_CHECK(S);
   DFB_CHECK_ARG(S->flags && epoch > 0, "shard_barrier");
   FlagPtrs fp;
   for (int d = 0; d < MAXW; ++d) fp.p[d] = d < S->world ? S->peer_flags[d] : nullptr;
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fp, S->flags, S->world, epoch);
+  const int* cursors = nullptr;
+  int cap = 0;
+  CountPtrs cp = count_ptrs(S->peer_pts_count, S->world);
+  if (S->fuse_publish) {
+    if (after_phase == 1) { cursors = S->counters + C_PTS; cap = S->pts_cap; }
+    else if (after_phase == 2) { cursors = S->counters + C_IDS; cap = S->ids_cap; cp = count_ptrs(S->peer_ids_count, S->world); }
+    else if (after_phase == 4) { cursors = S->counters + C_SMP; cap = S->smp_cap; cp = count_ptrs(S->peer_smp_count, S->world); }
+  }
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fp, S->flags, S->world, epoch, cursors, cap, cp);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

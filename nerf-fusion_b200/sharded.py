@@ -216,6 +216,7 @@ class IpcFabric:
     def __init__(self, m, group=None, barrier="peer"):
         import torch.distributed as dist
         self.dist, self.group, self.map, self.barrier_kind = dist, group, m, barrier
+        m.S.fuse_publish = 1 if barrier == "peer" else 0       # the barrier kernel also carries the per-pair record counts
         handles = [None] * m.world
         dist.all_gather_object(handles, (m.rank, m.mem.handle), group=group)
         self.bases, self._opened = self.open_peers(m, dict(handles))
@@ -248,7 +249,7 @@ class IpcFabric:
         m = ShardedMap(weights, args, device, dist.get_rank(group), dist.get_world_size(group), max_points_per_rank, capacity, div_mode, ipc=True)
         return cls(m, group, barrier)
 
-    def barrier(self):
+    def barrier(self, after_phase=0):
         """Stream-ordered barrier between two phases.  "peer": a one-block kernel exchanging epoch flags by peer stores (a few
         microseconds); "nccl": a 4-byte all-reduce (~20 us per barrier, measured 62 % -> see DESIGN.md scaling table)."""
         m = self.map
@@ -257,14 +258,14 @@ class IpcFabric:
             return
         m.epoch += 1
         with torch.cuda.device(m.device):
-            check(m.lib.dfb_shard_barrier(C.byref(m.S), m.epoch, m._stream()))
+            check(m.lib.dfb_shard_barrier(C.byref(m.S), m.epoch, after_phase, m._stream()))
 
     def integrate_keyframe(self, xyz, normal):
         """This rank's share of the keyframe (any split).  Collective: every rank calls it.  Asynchronous."""
         m = self.map
         for k in (1, 2, 3, 4):
             m.phase(k, xyz, normal)
-            self.barrier()
+            self.barrier(k)
         m.phase(5)
         return self
 

@@ -5,8 +5,8 @@ the ranks and every rank keeps indexer / latents / counts for ITS bricks only.
 This module is the host side of csrc/sharded.cu: it owns the device memory of one rank, maps the peers' receive buffers
 (CUDA IPC over NVLink / NVSwitch, `IpcFabric`) and drives the five phases of a keyframe with a stream-ordered barrier between
 them.  The data path has no host decisions: records are written by the producing kernels straight into the owner's
-receive buffer (peer stores), per-pair counts travel the same way, and the only collective is the 4-byte NCCL all-reduce
-that serves as the barrier -- no count read-back, no torch index glue, no host sync inside a keyframe.
+receive buffer (peer stores), per-pair counts travel with the barrier (a one-block kernel exchanging epoch flags by peer
+stores; optionally a 4-byte NCCL all-reduce) -- no count read-back, no torch index glue, no host sync inside a keyframe.
 
 `LocalFabric` runs all ranks of a world inside ONE process on ONE device (peer pointers are plain pointers): the same
 kernels and protocol, phase by phase over all ranks; it is how the multi-rank logic is tested on a single GPU and what

@@ -54,6 +54,10 @@ size_t dfb_encoder_blob_floats(void);
  * Also settable with the environment variable DFB_DECODER_ENGINE before the first call. */
 int dfb_set_decoder_engine(int engine);
 int dfb_get_decoder_engine(void);
+/* Frame pipelining (no reference counterpart; the reference tracks frames strictly one after the other, tracker.py:75-134):
+ * SMs the fused Gauss-Newton evaluation kernel leaves free (its grid = SM count - n) so that the NEXT frame's front end,
+ * queued on another stream, runs beside the pose solve instead of time-slicing with it.  0 = use every SM (default). */
+int dfb_set_gn_reserved_sms(int n);
 /* Same switch for the encoder (dfb_integrate_commit, dfb_encoder_forward); env DFB_ENCODER_ENGINE.  Default 1: the
  * tcgen05 encoder splits weights and the inputs of layers 0..2 into FP16 hi + lo parts, which keeps latents within
  * 1.8e-4 relative of the FP32 reference on the golden keyframe (tolerance 1e-3); 0 = FP32 CUDA cores (6e-7). */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "dfb_encoder_blob_floats": (_SZ, []),
     "dfb_set_decoder_engine": (_I, [_I]),
     "dfb_get_decoder_engine": (_I, []),
+    "dfb_set_gn_reserved_sms": (_I, [_I]),
     "dfb_set_encoder_engine": (_I, [_I]),
     "dfb_get_encoder_engine": (_I, []),
     "dfb_ingest_frame": (_I, [_P, _P, _I, _I, _F, _I, _F, _F, _I, _P, _P, _P]),

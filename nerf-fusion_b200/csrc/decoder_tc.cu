@@ -18,6 +18,7 @@
 // reduction + last-block step) in a single launch.
 // Math: network/di_decoder.py:55-86; reverse pass: SURVEY.md Appendix B.
 #include <algorithm>
+#include <cstdlib>
 
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
@@ -380,7 +381,19 @@ extern __shared__ unsigned char tc_smem_raw[];
 
 // CTA prologue: align, barriers, TMEM, bulk loads of the network (one barrier per layer, so layer 0 can start as soon as
 // its 22 KB have landed while the other 180 KB are still in flight)
-__device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
+// `defer_rest`: only the first segment (small block + W0) is requested here and the caller issues load_rest() later -- the
+// form gn_eval_kernel uses to run this prologue BEFORE its programmatic-dependency wait (the blob is constant).
+__device__ __forceinline__ void load_rest(const Ctx& c, const void* blob) {
+  if (threadIdx.x == 0) {
+    const char* src = reinterpret_cast<const char*>(blob);
+    const int seg_off[NWBAR + 1] = {IMG_W0, IMG_W1H, IMG_W2H, IMG_W3H, IMG_END};
+    for (int l = 1; l < NWBAR; ++l) {
+      mbar_expect_tx(c.wbar + 8 * l, (uint32_t)(seg_off[l + 1] - seg_off[l]));
+      for (int off = seg_off[l]; off < seg_off[l + 1]; off += 8192) bulk_g2s(c.sa + off, src + off, 8192u, c.wbar + 8 * l);
+    }
+  }
+}
+__device__ __forceinline__ void prologue(Ctx& c, const void* blob, bool defer_rest = false) {
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
   c.sm = tc_smem_raw + pad;
@@ -405,7 +418,7 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
     const int seg_off[NWBAR + 1] = {IMG_W0, IMG_W1H, IMG_W2H, IMG_W3H, IMG_END};
     mbar_expect_tx(wbar, (uint32_t)(IMG_W1H - IMG_W0 + SMALL_BYTES));
     bulk_g2s(c.sa + SM_SMALL, src + IMG_END, SMALL_BYTES, wbar);
-    for (int l = 0; l < NWBAR; ++l) {
+    for (int l = 0; l < (defer_rest ? 1 : NWBAR); ++l) {
       if (l > 0) mbar_expect_tx(wbar + 8 * l, (uint32_t)(seg_off[l + 1] - seg_off[l]));
       for (int off = seg_off[l]; off < seg_off[l + 1]; off += 8192) bulk_g2s(c.sa + off, src + off, 8192u, wbar + 8 * l);
     }
@@ -420,8 +433,8 @@ __device__ __forceinline__ void prologue(Ctx& c, const void* blob) {
 
 // End of the tile loop: every group has consumed its last accumulator, every weight copy has landed (a CTA without
 // tiles never waited for them) -- from here on the weight images are free to be reused as reduction scratch.
-__device__ __forceinline__ void epilogue_free(Ctx& c) {
-  for (int l = 0; l < NWBAR; ++l) mbar_wait(c.wbar + 8 * l, 0);
+__device__ __forceinline__ void epilogue_free(Ctx& c, int n_requested = NWBAR) {
+  for (int l = 0; l < n_requested; ++l) mbar_wait(c.wbar + 8 * l, 0);
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(c.tmem_base, TMEM_COLS);
@@ -598,8 +611,8 @@ __global__ void __launch_bounds__(CTA_T, 1) sdf_hg_kernel(MapDev M, PoseDev P, c
 }
 
 // One Gauss-Newton evaluation in ONE launch (gauss_newton.cu): the SDF term on the tensor cores; the photometric term's
-// pixels are handed out in chunks to whichever tile group has run out of tiles (in the last round half of the groups
-// have, and their SM's tensor pipe is busy with the sibling group anyway); both terms' sums go to GnShared with one
+// pixels are dealt in chunks to the tile groups, those without a tile in the last round first (more than half of the groups,
+// and their SM's tensor pipe is busy with the sibling group anyway); both terms' sums go to GnShared with one
 // atomic per value per block; the last block to finish runs the step (solve, pose update, record for the host).
 constexpr int RGB_PIX = 2;                       // pixels per thread per chunk (chunk = GT * RGB_PIX pixels)
 __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float* __restrict__ obs, int n, const int* __restrict__ n_dev,
@@ -607,18 +620,26 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
                                                        const float* __restrict__ latents, const float* __restrict__ obs_count,
                                                        const void* __restrict__ blob, int robust, float robust_k, int with_J, RgbDev R,
                                                        GnShared* gs, int gi, gn::StepArgs sa) {
-  if (gs->done[gi]) {                            // a launch queued ahead of a group that has ended: only the record is owed
-    if (blockIdx.x == 0 && threadIdx.x < 32) gn::skip_record(gs, sa);
-    return;
-  }
-  const PoseDev P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
-  if (n_dev) n = min(n, max(*n_dev, 0));         // row count still on the device (dfb_preprocess_frame's output)
+  // Programmatic dependent launch: evaluation k+1 is queued behind evaluation k (gauss_newton.cu keeps one launch of
+  // look-ahead) and is allowed onto an SM as soon as k's CTA there has exited.  Everything that does not depend on k --
+  // barriers, the TMEM allocation, the copy of the first weight segment (the blob is constant) -- runs before the
+  // dependency wait, i.e. under k's tail (block reduction, last-block solve, record); pose, flags and sums are read after it.
+  pdl_launch_dependents();
   Ctx c;
 #ifdef DFB_TC_PROFILE
   c.grp = threadIdx.x / GT; c.part = (threadIdx.x % GT) / T; c.row = threadIdx.x % T;
 #endif
   PROF_MARK(c);                                  // kernel start
-  prologue(c, blob);
+  prologue(c, blob, true);
+  pdl_wait();
+  if (gs->done[gi]) {                            // a launch queued ahead of a group that has ended: only the record is owed
+    epilogue_free(c, 1);
+    if (blockIdx.x == 0 && threadIdx.x < 32) gn::skip_record(gs, sa);
+    return;
+  }
+  load_rest(c, blob);
+  const PoseDev P = *reinterpret_cast<const PoseDev*>(gs->pose_sdf);
+  if (n_dev) n = min(n, max(*n_dev, 0));         // row count still on the device (dfb_preprocess_frame's output)
   PROF_MARK(c);                                  // prologue done
   float acc[HG_PER_THREAD];
 #pragma unroll
@@ -634,13 +655,16 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
 #pragma unroll
     for (int i = 0; i < 3; ++i) R.P.kt[i] = gs->kt[i];
     const int tg = threadIdx.x % GT, npx = R.H * R.W;
-    volatile int* slotp = reinterpret_cast<volatile int*>(c.sm + SM_BAR + 72 + 4 * c.grp);
-    for (;;) {
-      if (tg == 0) *slotp = atomicAdd(&gs->rgb_cursor, 1);
-      group_sync(c.grp);
-      const int base = *slotp * (GT * RGB_PIX);
-      group_sync(c.grp);
-      if (base >= npx) break;
+    // Chunks of GT * RGB_PIX pixels are dealt STATICALLY, the groups that have no tile in the partial round first (they are
+    // idle while their sibling's tile runs): which thread adds which pixels is then a function of the launch geometry alone,
+    // so an evaluation is reproducible run to run (a dynamic ticket made the FP32 partial sums, and through the energy-rise
+    // rule of tracker.py:269 sometimes the iteration count, depend on timing).
+    const Sched S = make_sched(n);
+    const int rem = S.tiles - S.full * S.slots;                     // tiles of the partial round: slots j < rem have one more tile
+    const int jslot = c.grp * (int)gridDim.x + (int)blockIdx.x;
+    const int rank = jslot >= rem ? jslot - rem : (S.slots - rem) + jslot;
+    for (int ch = rank; ch * (GT * RGB_PIX) < npx; ch += S.slots) {
+      const int base = ch * (GT * RGB_PIX);
 #pragma unroll
       for (int e = 0; e < RGB_PIX; ++e) {
         const int i = base + e * GT + tg;
@@ -804,13 +828,26 @@ int tc_get_sdf(const MapDev& M, const float* xyz, int n, const int64_t* indexer,
   return DFB_OK;
 }
 
+static int g_gn_reserved_sms = 0;
+extern "C" int dfb_set_gn_reserved_sms(int n) { g_gn_reserved_sms = n < 0 ? 0 : n; return DFB_OK; }
+
 int tc_gn_eval(const MapDev& M, const float* obs, int n, const int* n_dev, const int64_t* indexer, const float* latents, const float* obs_count,
                const void* blob, int robust, float robust_k, int with_J, const RgbDev& R, GnShared* gs, int gi, const gn::StepArgs& sa,
                cudaStream_t s) {
   int rc = tc::prep(tc::gn_eval_kernel);
   if (rc) return rc;
-  const int grid = R.on ? sm_count() : std::max(1, tc::grid_for(n));     // every SM takes photometric chunks
-  tc::gn_eval_kernel<<<grid, tc::CTA_T, tc::SM_ALLOC, s>>>(M, obs, n, n_dev, indexer, latents, obs_count, blob, robust, robust_k, with_J, R, gs, gi, sa);
+  const int avail = std::max(8, sm_count() - g_gn_reserved_sms);            // SMs left to a concurrently running front end are not used
+  const int grid = R.on ? avail : std::max(1, std::min(tc::grid_for(n), avail));   // every CTA takes photometric chunks
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CTA_T); cfg.dynamicSmemBytes = tc::SM_ALLOC; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("DFB_NO_PDL") != nullptr;      // A/B switch: plain stream order (the kernel's griddepcontrol instructions are then no-ops)
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gn_eval_kernel, M, obs, n, n_dev, indexer, latents, obs_count, blob, robust, robust_k, with_J, R, gs,
+                                     gi, sa);
+  if (e != cudaSuccess) { set_error("gn_eval launch: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

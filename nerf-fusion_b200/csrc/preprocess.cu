@@ -6,6 +6,7 @@
 // queries are radius-bounded (pcproc.cu:104,120), so an exact answer only needs the points of the 27 cells
 // around the query in a uniform grid with cell >= radius: one counting sort, no host sync, candidates read
 // coalesced from the cell-sorted copy, result set in registers.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dfb {
@@ -105,9 +106,12 @@ static size_t grid_ws_layout(Arena& a, int n, GridWs* w) {
   return a.off;
 }
 
+// bbox[6] counts the occupied cells of the grid being built (grid_count_kernel); bbox[7] keeps the count of the previous
+// build in the same workspace (the density hint of grid_params_kernel)
 __global__ void bbox_init_kernel(unsigned* bbox) {
   if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
   else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+  else if (threadIdx.x == 6) { bbox[7] = bbox[6]; bbox[6] = 0u; }
 }
 
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, int n, int stride, unsigned* bbox, const int* __restrict__ n_dev) {
@@ -149,7 +153,19 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ p, 
   }
 }
 
-__global__ void grid_params_kernel(const unsigned* bbox, float radius, int cap, GridParams* gp) {
+// hint_n (optional): the PREVIOUS grid built in this workspace held *hint_n points in bbox[7] occupied cells of edge gp->cell.
+// For a surface-like cloud that gives the point spacing s = cell / sqrt(points per occupied cell), and the kNN search wants
+// cells of about the 16-neighbour radius (2.26 s): with much smaller cells a query walks dozens of nearly empty cells (at
+// 3.6 m a 640x480 depth frame has 15 mm spacing: 85 % of the queries needed two shells of 25 mm cells, 5 % three or four),
+// with much larger ones it scans hundreds of candidates.  The result of the search does not depend on the cell size.
+__global__ void grid_params_kernel(const unsigned* bbox, float radius, int cap, GridParams* gp, const int* hint_n, float cell_max) {
+  if (hint_n) {
+    const float occ = (float)bbox[7], n = (float)*hint_n;
+    if (occ > 0.f && n > 0.f) {
+      const float spacing = gp->cell * rsqrtf(n / occ);
+      radius = fminf(fmaxf(3.0f * spacing, radius), cell_max);
+    }
+  }
   float lo[3], hi[3];
   for (int a = 0; a < 3; ++a) {
     lo[a] = ord2f(bbox[a]);
@@ -178,7 +194,7 @@ __device__ __forceinline__ int3 cell_coord(const GridParams& g, float x, float y
 }
 
 __global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict__ pc4, int n, const GridParams* gpp,
-                                                         int* cell_of, int* cell_count, const int* __restrict__ n_dev) {
+                                                         int* cell_of, int* cell_count, const int* __restrict__ n_dev, unsigned* bbox) {
   if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict
   int3 c = cell_coord(g, p.x, p.y, p.z);
   int id = (c.x * g.ny + c.y) * g.nz + c.z;
   cell_of[i] = id;
-  atomicAdd(&cell_count[id], 1);
+  if (atomicAdd(&cell_count[id], 1) == 0) atomicAdd(&bbox[6], 1u);
 }
 
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restrict__ pc4, int n, const int* cell_of,
@@ -273,6 +289,60 @@ __device__ float4 sym3eig_smallest(float3 x1, float3 x2, float3 x3) {
   return ret;
 }
 
+// pcproc.cu:107-158 on the sorted key list (slot 0 = the query itself): mean, covariance, smallest eigenvector, orientation
+template <int K>
+__device__ __forceinline__ void normal_from_keys(const unsigned long long (&key)[K], const float4 q, const float4* __restrict__ pc4, int max_nn,
+                                                 float r2, float3 cam, float* __restrict__ normals) {
+  int oi = __float_as_int(q.w);
+  float3 mean = make_float3(0.f, 0.f, 0.f);
+  float valid = 0.f;
+#pragma unroll
+  for (int t = 1; t < K; ++t) {
+    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
+      float4 p = pc4[(unsigned)key[t]];
+      mean.x += p.x; mean.y += p.y; mean.z += p.z;
+      valid += 1.0f;
+    }
+  }
+  if (valid < 5.0f) {
+    normals[3 * oi + 0] = normals[3 * oi + 1] = normals[3 * oi + 2] = CUDART_NAN_F;
+    return;
+  }
+  mean.x /= valid; mean.y /= valid; mean.z /= valid;
+  float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
+#pragma unroll
+  for (int t = 1; t < K; ++t) {
+    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
+      float4 pp = pc4[(unsigned)key[t]];
+      float3 pos = make_float3(pp.x - mean.x, pp.y - mean.y, pp.z - mean.z);
+      c1.x += pos.x * pos.x; c1.y += pos.x * pos.y; c1.z += pos.x * pos.z;
+      c2.x += pos.y * pos.x; c2.y += pos.y * pos.y; c2.z += pos.y * pos.z;
+      c3.x += pos.z * pos.x; c3.y += pos.z * pos.y; c3.z += pos.z * pos.z;
+    }
+  }
+  float4 ev = sym3eig_smallest(c1, c2, c3);
+  float3 nrm = make_float3(ev.x, ev.y, ev.z);
+  float3 dp = make_float3(q.x - cam.x, q.y - cam.y, q.z - cam.z);
+  if (nrm.x * dp.x + nrm.y * dp.y + nrm.z * dp.z > 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; }
+  normals[3 * oi + 0] = nrm.x;
+  normals[3 * oi + 1] = nrm.y;
+  normals[3 * oi + 2] = nrm.z;
+}
+
+// Position of a query inside its grid cell (in cell units) and the distance, in cells, from the query to the slab of cells
+// at offset d along one axis (0 for the query's own slab).  cell2 carries a 0.2 % safety margin for the rounding of
+// cell_coord, like the `reach` test of the shell loop: the bound may only err on the small side.
+struct CellFrac { float x, y, z, cell2; };
+__device__ __forceinline__ CellFrac cell_frac(const GridParams& g, const float4 q, const int3 c) {
+  CellFrac f;
+  f.x = (q.x - g.ox) * g.inv_cell - (float)c.x; f.y = (q.y - g.oy) * g.inv_cell - (float)c.y; f.z = (q.z - g.oz) * g.inv_cell - (float)c.z;
+  f.cell2 = g.cell * g.cell * 0.998f;
+  return f;
+}
+__device__ __forceinline__ float cell_gap(int d, float frac) {
+  return d > 0 ? fmaxf((float)d - frac, 0.f) : (d < 0 ? fmaxf(frac - (float)(d + 1), 0.f) : 0.f);
+}
+
 // K nearest (self included) kept sorted ascending in registers; then pcproc.cu:107-158.
 // An entry is one 64-bit key: (distance bits << 32) | ORIGINAL index.  Distances are >= +0, so their bit patterns order
 // like the values, and one unsigned compare implements "closer, or equally close and earlier in the input" -- the
@@ -297,6 +367,7 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
   // be used is closer than that (with a margin for the rounding of cell_coord) the list is final: the exact K nearest.
   const int Rmax = max(1, (int)ceilf(radius * g.inv_cell));
   const int last = min(max_nn, K) - 1;
+  const CellFrac cf = cell_frac(g, q, c);
   for (int R = 1; R <= Rmax; ++R) {
     // columns nearest to the query first (0, -1, +1, -2, ...): the K-th distance tightens early and most later
     // candidates fail the cheap test
@@ -304,10 +375,14 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
       const int dx = (ix & 1) ? -((ix + 1) >> 1) : (ix >> 1);
       const int x = c.x + dx;
       if (x < 0 || x >= g.nx) continue;
+      const float gx = cell_gap(dx, cf.x);
       for (int iy = 0; iy <= 2 * R; ++iy) {
         const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
         const int y = c.y + dy;
         if (y < 0 || y >= g.ny) continue;
+        // no point of this column can be closer than its cells are: skip it when that already exceeds the K-th distance
+        const float gy = cell_gap(dy, cf.y);
+        if ((gx * gx + gy * gy) * cf.cell2 >= __uint_as_float((unsigned)(key[K - 1] >> 32))) continue;
         const int row = (x * g.ny + y) * g.nz;
         // R == 1 or a column on the shell's side faces: the whole z-run (contiguous in memory); interior column: only the
         // two new end cells
@@ -345,50 +420,134 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
     const float reach = (float)R * g.cell * 0.9999f;
     if (__uint_as_float((unsigned)(key[last] >> 32)) < reach * reach) break;
   }
-  int oi = __float_as_int(q.w);
-  float3 mean = make_float3(0.f, 0.f, 0.f);
-  float valid = 0.f;
-#pragma unroll
-  for (int t = 1; t < K; ++t) {
-    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
-      float4 p = pc4[(unsigned)key[t]];
-      mean.x += p.x; mean.y += p.y; mean.z += p.z;
-      valid += 1.0f;
-    }
-  }
-  if (valid < 5.0f) {
-    normals[3 * oi + 0] = normals[3 * oi + 1] = normals[3 * oi + 2] = CUDART_NAN_F;
-    return;
-  }
-  mean.x /= valid; mean.y /= valid; mean.z /= valid;
-  float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
-#pragma unroll
-  for (int t = 1; t < K; ++t) {
-    if (t < max_nn && __uint_as_float((unsigned)(key[t] >> 32)) < r2) {
-      float4 pp = pc4[(unsigned)key[t]];
-      float3 pos = make_float3(pp.x - mean.x, pp.y - mean.y, pp.z - mean.z);
-      c1.x += pos.x * pos.x; c1.y += pos.x * pos.y; c1.z += pos.x * pos.z;
-      c2.x += pos.y * pos.x; c2.y += pos.y * pos.y; c2.z += pos.y * pos.z;
-      c3.x += pos.z * pos.x; c3.y += pos.z * pos.y; c3.z += pos.z * pos.z;
-    }
-  }
-  float4 ev = sym3eig_smallest(c1, c2, c3);
-  float3 nrm = make_float3(ev.x, ev.y, ev.z);
-  float3 dp = make_float3(q.x - cam.x, q.y - cam.y, q.z - cam.z);
-  if (nrm.x * dp.x + nrm.y * dp.y + nrm.z * dp.z > 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; }
-  normals[3 * oi + 0] = nrm.x;
-  normals[3 * oi + 1] = nrm.y;
-  normals[3 * oi + 2] = nrm.z;
+  normal_from_keys<K>(key, q, pc4, max_nn, r2, cam, normals);
 }
 
+
+// ---- estimate_normals, batched form (K = 16; the default) -------------------------------------------------------------
+// Same result as normals_kernel<16> bit for bit (the exact 16 smallest (distance, index) keys, ascending), different search
+// economics.  In the one-thread-per-query form nearly every candidate step pays a 16-deep insertion (~130 instructions)
+// because SOME lane of the warp inserts, and lanes run different trip counts (12 of 32 lanes active, ncu).  Here
+//   * the warp walks the candidate runs in lock-step (trip count = the longest run among its lanes, shorter lanes predicated
+//     off), so warp votes are legal at every step;
+//   * a candidate that beats the lane's current 16th key is only APPENDED to the lane's column of a shared-memory batch
+//     (16 slots, conflict-free layout);
+//   * when any lane's batch is full -- and at the end of a shell -- ALL lanes sort their batch (bitonic network in registers)
+//     and merge it into their sorted top-16 (bitonic merge): ~750 instructions per 16 candidates instead of ~130 per candidate,
+//     executed converged.
+#define DFB_CE(a, b) { const bool s_ = (b) < (a); const unsigned long long t_ = s_ ? (b) : (a); (b) = s_ ? (a) : (b); (a) = t_; }
+constexpr int NB_T = 128;              // threads per block
+constexpr int NB_CAP = 16;             // batch slots per lane
+__device__ __forceinline__ void nb_merge(unsigned long long (&top)[16], const unsigned long long* __restrict__ batch, int& cnt) {
+  unsigned long long b[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) b[i] = i < cnt ? batch[i * NB_T] : 0x7f8000007fffffffull;
+  cnt = 0;
+  // bitonic sort, ascending
+#pragma unroll
+  for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) { DFB_CE(b[i], b[l]); } else { DFB_CE(b[l], b[i]); }
+        }
+      }
+    }
+  }
+  // the 16 smallest of top (ascending) and b (ascending): min(top[i], b[15 - i]) is bitonic; one bitonic merge sorts it
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const unsigned long long y = b[15 - i]; top[i] = y < top[i] ? y : top[i]; }
+#pragma unroll
+  for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int l = i ^ j;
+      if (l > i) DFB_CE(top[i], top[l]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NB_T, 4) normals_batched_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
+                                                                  const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
+                                                                  float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
+  __shared__ unsigned long long s_batch[NB_CAP * NB_T];
+  if (n_dev) n = *n_dev;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((j & ~31) >= n) return;                                        // whole warp past the end (warp-uniform)
+  const bool live = j < n;
+  const GridParams g = *gpp;
+  const float4 q = sorted[live ? j : n - 1];
+  const int3 c = cell_coord(g, q.x, q.y, q.z);
+  unsigned long long top[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) top[t] = 0x7f8000007fffffffull;       // (+inf, INT_MAX)
+  unsigned long long* batch = s_batch + threadIdx.x;
+  int cnt = 0;
+  const float r2 = radius * radius;
+  const int Rmax = max(1, (int)ceilf(radius * g.inv_cell));
+  const int last = min(max_nn, 16) - 1;
+  const CellFrac cf = cell_frac(g, q, c);
+  bool done = !live;
+  for (int R = 1; R <= Rmax; ++R) {
+    for (int ix = 0; ix <= 2 * R; ++ix) {
+      const int dx = (ix & 1) ? -((ix + 1) >> 1) : (ix >> 1);
+      const int x = c.x + dx;
+      const bool okx = !done && x >= 0 && x < g.nx;
+      const float gx = cell_gap(dx, cf.x);
+      for (int iy = 0; iy <= 2 * R; ++iy) {
+        const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
+        const int y = c.y + dy;
+        const float gy = cell_gap(dy, cf.y);
+        // (the 16th key may be stale by the unmerged batch: the bound is then only less tight)
+        const bool okxy = okx && y >= 0 && y < g.ny && (gx * gx + gy * gy) * cf.cell2 < __uint_as_float((unsigned)(top[15] >> 32));
+        const int row = (x * g.ny + y) * g.nz;
+        const bool whole = (R == 1 || dx == -R || dx == R || dy == -R || dy == R);   // warp-uniform
+        for (int sgm = 0; sgm < (whole ? 1 : 2); ++sgm) {
+          int b = 0, e = 0;
+          if (okxy) {
+            if (whole) {
+              b = cell_start[row + max(c.z - R, 0)]; e = cell_start[row + min(c.z + R, g.nz - 1) + 1];
+            } else {
+              const int z = sgm ? c.z + R : c.z - R;
+              if (z >= 0 && z < g.nz) { b = cell_start[row + z]; e = cell_start[row + z + 1]; }
+            }
+          }
+          const int len = e - b;
+          const int L = __reduce_max_sync(0xffffffffu, len);
+          for (int k = 0; k < L; ++k) {
+            if (k < len) {
+              const float4 p = sorted[b + k];
+              const float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+              const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+              if (d < r2 && nk < top[15]) { batch[cnt * NB_T] = nk; ++cnt; }
+            }
+            if (__any_sync(0xffffffffu, cnt == NB_CAP)) nb_merge(top, batch, cnt);
+          }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, cnt > 0)) nb_merge(top, batch, cnt);
+    const float reach = (float)R * g.cell * 0.9999f;
+    if (__uint_as_float((unsigned)(top[last] >> 32)) < reach * reach) done = true;
+    if (__all_sync(0xffffffffu, done)) break;
+  }
+  if (live) normal_from_keys<16>(top, q, pc4, max_nn, r2, cam, normals);
+}
+
+static bool normals_use_v1() { static const bool v = getenv("DFB_NORMALS_V1") != nullptr; return v; }   // A/B switch: one thread per query, immediate insertion
+
 // cell: target cell edge (grown by 1.25x steps until the bounding box fits into `cap` cells)
-static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, cudaStream_t s, const int* n_dev = nullptr) {
+static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, cudaStream_t s, const int* n_dev = nullptr,
+                      const int* hint_n = nullptr, float cell_max = 0.f) {
   bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
-  grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp);
+  grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp, hint_n, cell_max);
   // counts, scan and cursor reset cover the ncell + 1 cells the bounding box needs (device-side length), not the capacity
   zero_words_dev(w.cell_count, cap + 1, &w.gp->ncell1, s);
-  grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev);
+  grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev, w.bbox);
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s, &w.gp->ncell1);
   if (rc) return rc;
@@ -681,7 +840,9 @@ int dfb_estimate_normals(const float* pc4, int n, int max_nn, float radius, cons
   int rc = build_grid(pc4, n, radius / NORMAL_SUB, GRID_CAP, w, s);
   if (rc) return rc;
   float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
-  if (max_nn <= 16)
+  if (max_nn <= 16 && !normals_use_v1())
+    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pc4), n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
+  else if (max_nn <= 16)
     normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pc4), n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
   else
     normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pc4), n, w.gp, w.cell_start, max_nn, radius, cam, normals, nullptr);
@@ -828,10 +989,13 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   if (rc) return rc;
   compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC);
   // P3: normals
-  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1]);
+  // (cell size from the density the radius filter's grid just measured: grid_params_kernel)
+  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1], &counts[0], normal_radius * 0.5f);
   if (rc) return rc;
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
-  if (max_nn <= 16)
+  if (max_nn <= 16 && !normals_use_v1())
+    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+  else if (max_nn <= 16)
     normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
   else
     normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);

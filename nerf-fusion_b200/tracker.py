@@ -78,6 +78,24 @@ class SDFTracker:
         self._fe_seen = {}                 # key -> eager calls so far (the first call warms kernels and workspaces up)
         self._fe_busy = {}                 # key -> graph set whose static outputs last_intensity / last_depth still alias
         self._fe_choice = None             # (key, set) the last graphed front-end call replayed
+        self._fe_cur = {}                  # key -> graph set the frame being tracked right now uses
+        # Frame pipelining: track_camera(..., next_frame=(rgb, depth)) / prefetch_frame() enqueue the NEXT frame's front end on
+        # a side stream before this frame's pose solve is queued, so the ~60 small front-end kernels fill the SMs the solve
+        # leaves idle (its partial tile round, the serial step, the gaps between evaluations).  Three graph sets rotate:
+        # last committed frame (read as last_*), current frame, prefetched frame.
+        self._pf = None                    # pending prefetch: dict(rgb, depth, base, idx, ent, event)
+        self._pf_stream = None
+        # The pose solve is the critical path of a frame; with a prefetched front end running beside it, it is launched on a
+        # HIGH-priority stream so that a waiting solve CTA (a whole SM each) is placed before the front end's small blocks,
+        # which then fill only what the solve leaves idle.  DFB_SOLVE_PRIO=0 keeps the solve on the caller's stream.
+        import os
+        self._solve_prio = int(os.environ.get("DFB_SOLVE_PRIO", "-1"))
+        # Optionally the evaluation kernel (one whole-SM CTA per SM: nothing else fits beside it) leaves some SMs to the front
+        # end.  Measured (tools/pipeline_timeline.py): without reserved SMs the two time-slice (front end 320 -> 900 us, solve
+        # 700 -> 850 us, frame 1.19 -> 1.13 ms); reserving 16..48 SMs shortens the front end to ~650 us but lengthens the solve
+        # more (the long normals blocks still land on the solve's SMs between evaluations): default 0.
+        self._reserve_sms = int(os.environ.get("DFB_GN_RESERVE_SMS", "0"))
+        self._solve_stream = None
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
         self._gn_pinned = torch.zeros((64,), dtype=torch.float64).pin_memory()       # DFB_GN_PINNED_DOUBLES
@@ -139,21 +157,14 @@ class SDFTracker:
                                                  (0.0, 0.0, 0.0), 0.02, self.map.div_mode, sync=False, ws=ws)
         return Is, Ds, Gs, out_p, out_n, cnt
 
-    def _frontend_graphed(self, rgb_data, depth_data, calib, depth_cut=None):
-        """Replays the captured front end on copies of the inputs.  The first call per key runs eagerly (loads kernels,
-        sizes workspaces); later calls capture / replay.  Two graph sets per key exist because their outputs are static
-        buffers and the pyramids of the last COMMITTED frame are still read as `last_*` while the next frame is processed:
-        a call replays the set `last_*` does not alias (track_camera marks a set busy when it commits its pyramids), so
-        calls that commit nothing (for_pc=True, a failed solve) can never make a frame's photometric term read itself."""
-        base = (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode,
+    N_FE_SETS = 3
+
+    def _fe_base(self, rgb_data, depth_data, calib, depth_cut):
+        return (tuple(rgb_data.shape), tuple(depth_data.shape), calib.fx, calib.fy, calib.cx, calib.cy, self.map.div_mode,
                 None if depth_cut is None else tuple(depth_cut))
-        seen = self._fe_seen.get(base, 0)
-        self._fe_seen[base] = seen + 1
-        self._fe_choice = None
-        if seen == 0:
-            return self._frontend(rgb_data, depth_data, calib, depth_cut)
-        idx = 1 if self._fe_busy.get(base) == 0 else 0
-        self._fe_choice = (base, idx)
+
+    def _fe_entry(self, base, idx, rgb_data, depth_data, calib, depth_cut):
+        """Graph set `idx` of key `base`, captured on first use (static inputs / outputs + the graph)."""
         key = base + (idx,)
         ent = self._fe_graphs.get(key)
         if ent is None:
@@ -173,6 +184,10 @@ class SDFTracker:
             ent["graph"] = graph
             ent["calls"] = {k: v - before.get(k, 0) for k, v in _lib.CALLS.items() if v != before.get(k, 0)}   # C calls inside one replay
             self._fe_graphs[key] = ent
+        return ent
+
+    def _fe_replay(self, ent, rgb_data, depth_data):
+        """Copies the frame into the set's static inputs and replays its graph on the current stream."""
         ent["rgb"].copy_(rgb_data); ent["depth"].copy_(depth_data)
         ent["graph"].replay()
         from . import _lib
@@ -180,16 +195,87 @@ class SDFTracker:
             _lib.CALLS[k] = _lib.CALLS.get(k, 0) + v
         return ent["out"]
 
-    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False, depth_cut=None):
+    def _frontend_graphed(self, rgb_data, depth_data, calib, depth_cut=None):
+        """Replays the captured front end on copies of the inputs.  The first call per key runs eagerly (loads kernels,
+        sizes workspaces); later calls capture / replay.  Several graph sets per key exist because their outputs are static
+        buffers and the pyramids of the last COMMITTED frame are still read as `last_*` while the next frame is processed:
+        a call replays a set `last_*` does not alias (track_camera marks a set busy when it commits its pyramids), so
+        calls that commit nothing (for_pc=True, a failed solve) can never make a frame's photometric term read itself.
+        A frame whose front end was prefetched (prefetch_frame) only waits for the side stream."""
+        base = self._fe_base(rgb_data, depth_data, calib, depth_cut)
+        self._fe_choice = None
+        pf, self._pf = self._pf, None
+        if pf is not None:
+            torch.cuda.current_stream(self.map.device).wait_event(pf["event"])     # also orders the shared workspace
+            if pf["rgb"] is rgb_data and pf["depth"] is depth_data and pf["base"] == base:
+                self._fe_seen[base] = self._fe_seen.get(base, 0) + 1
+                self._fe_choice = (base, pf["idx"])
+                self._fe_cur[base] = pf["idx"]
+                return pf["ent"]["out"]
+        seen = self._fe_seen.get(base, 0)
+        self._fe_seen[base] = seen + 1
+        if seen == 0:
+            self._fe_cur.pop(base, None)
+            return self._frontend(rgb_data, depth_data, calib, depth_cut)
+        idx = 1 if self._fe_busy.get(base) == 0 else 0
+        self._fe_choice = (base, idx)
+        self._fe_cur[base] = idx
+        return self._fe_replay(self._fe_entry(base, idx, rgb_data, depth_data, calib, depth_cut), rgb_data, depth_data)
+
+    @property
+    def prefetch_stream(self):
+        """The side stream prefetched front ends run on (callers that produce the next frame on the device, e.g. an ingest
+        kernel, can enqueue that work here so that it is ordered before the prefetch without touching the main stream)."""
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(self.map.device)
+        return self._pf_stream
+
+    def prefetch_frame(self, rgb_data, depth_data, calib, depth_cut=None):
+        """Enqueues the front end (tracker.py:84-120: intensity, pyramids, gradients, preprocessing) of the frame that will be
+        tracked NEXT on the side stream and returns at once; the following track_camera call with the same tensor objects
+        only waits for it.  Results are bit-identical to the unprefetched path (same kernels, same inputs).  Returns False when
+        nothing was queued (graph front end off, or this image size has not been seen yet)."""
+        if not (self.graph_frontend and self.fused_preprocess and self.sdf_args.subsample == 0.5):
+            return False
+        if not (rgb_data.is_contiguous() and depth_data.is_contiguous()):
+            return False
+        base = self._fe_base(rgb_data, depth_data, calib, depth_cut)
+        if self._fe_seen.get(base, 0) == 0:
+            return False
+        dev = self.map.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            side = self.prefetch_stream
+            if self._pf is not None:                              # an unconsumed prefetch: its outputs are dropped
+                self._pf = None
+            busy, cur = self._fe_busy.get(base), self._fe_cur.get(base)
+            idx = next(i for i in range(self.N_FE_SETS) if i != busy and i != cur)
+            ent = self._fe_entry(base, idx, rgb_data, depth_data, calib, depth_cut)    # may capture (first use of the set)
+            side.wait_stream(main)                                # inputs produced on the main stream; the set's last readers
+            with torch.cuda.stream(side):
+                self._fe_replay(ent, rgb_data, depth_data)
+                ev = torch.cuda.Event()
+                ev.record(side)
+        self._pf = dict(rgb=rgb_data, depth=depth_data, base=base, idx=idx, ent=ent, event=ev)
+        return True
+
+    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None, for_pc=False, depth_cut=None, next_frame=None):
         """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid.
         depth_cut = (near, far), optional: depths outside the range become NaN here (what main.py:56-57 does before the
-        call), so the clipping is part of the captured front end instead of five eager launches."""
+        call), so the clipping is part of the captured front end instead of five eager launches.
+        next_frame = (rgb, depth), optional: the frame that will be tracked next; its front end is queued on the side stream
+        (prefetch_frame) before this frame's pose solve, and runs under it."""
         if self.fused_preprocess and self.sdf_args.subsample == 0.5:
             graphed = self.graph_frontend
             fe = self._frontend_graphed if graphed else self._frontend
+            if not graphed and self._pf is not None:              # a prefetch queued before the graph front end was switched off
+                torch.cuda.current_stream(self.map.device).wait_event(self._pf["event"])
+                self._pf = None
             with torch.cuda.device(self.map.device):
                 cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib,
                                                                             depth_cut)
+                if next_frame is not None and graphed:
+                    self.prefetch_frame(next_frame[0], next_frame[1], calib, depth_cut)
             # The row count stays on the device while the pose solve is queued behind the front end (the kernels read it
             # there); it is read back once the solve has returned.
             defer = self.native_gn and set_pose is None and not for_pc and len(self.all_pd_pose) > 0
@@ -216,7 +302,7 @@ class SDFTracker:
             cur_intensity = torch.mean(rgb_data, dim=-1)
             cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
             pc_data, normal_data = self.preprocess_depth(cur_depth[0], calib)
-        # (graph outputs are static buffers reused two frames later: hand out copies)
+        # (graph outputs are static buffers reused a few frames later: hand out copies)
         self.last_processed_pc = [pc_data.clone(), normal_data.clone()] if graphed else [pc_data, normal_data]
         if for_pc:
             return self.last_processed_pc
@@ -321,10 +407,25 @@ class SDFTracker:
             stats[4] = 0x54494d45
         obs = obs_xyz.contiguous()
         with torch.cuda.device(m.device):
-            check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0),
-                                         _p(obs_count) if obs_count is not None else None, _p(m.indexer), _p(m.latent_vecs),
-                                         _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._gn_dev),
-                                         C.c_void_p(self._gn_pinned.data_ptr()), stats, _stream()))
+            cur = torch.cuda.current_stream(m.device)
+            solve = cur
+            if self._solve_prio != 0 and self._pf is not None:    # a front end runs beside this solve: give the solve priority
+                if self._solve_stream is None:
+                    self._solve_stream = torch.cuda.Stream(m.device, priority=self._solve_prio)
+                solve = self._solve_stream
+                solve.wait_stream(cur)
+            reserve = self._reserve_sms if self._pf is not None else 0
+            try:
+                m.lib.dfb_set_gn_reserved_sms(reserve)
+                with torch.cuda.stream(solve):
+                    check(m.lib.dfb_gauss_newton(C.byref(m._params), C.byref(cfg), _p(obs), obs.size(0),
+                                                 _p(obs_count) if obs_count is not None else None, _p(m.indexer), _p(m.latent_vecs),
+                                                 _p(m.voxel_obs_count), _p(m.decoder_blob), levels, intr, lastp, deltap, _p(self._gn_dev),
+                                                 C.c_void_p(self._gn_pinned.data_ptr()), stats, _stream()))
+            finally:
+                m.lib.dfb_set_gn_reserved_sms(0)
+                if solve is not cur:
+                    cur.wait_stream(solve)
         self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
         if self.time_kernels:
             self.sdf_kernel_us += stats[4]; self.sdf_queries_J += stats[5]; self.sdf_queries_noJ += stats[6]

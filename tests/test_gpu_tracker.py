@@ -117,8 +117,11 @@ def test_native_gauss_newton_equals_python_loop(weights, T):
         poses[native] = (out, trk.n_sdf_evals, trk.n_rgb_evals)
     assert poses[True][1:] == poses[False][1:]                       # same number of evaluations = same accept/rollback path
     for (Ra, ta), (Rb, tb) in zip(poses[True][0], poses[False][0]):
-        # both drivers cast the f64 poses to fp32 for the kernels; 1-ulp differences there are the only divergence
-        assert np.abs(Ra - Rb).max() < 1e-6 and np.abs(ta - tb).max() < 1e-6
+        # both drivers cast the f64 poses to fp32 for the kernels; besides 1-ulp differences there, the fused evaluation hands
+        # the photometric pixels out dynamically (FP32 partial sums grouped differently run to run): over the 14 steps of this
+        # solve that moves the pose by up to ~3e-6 (measured: the 1e-6 bound failed in 3 of 6 runs), still below the
+        # north-star 1e-5
+        assert np.abs(Ra - Rb).max() < 1e-5 and np.abs(ta - tb).max() < 1e-5
 
 
 def test_graph_front_end_equals_eager(weights, T):
@@ -144,6 +147,48 @@ def test_graph_front_end_equals_eager(weights, T):
     assert len(trk_g._fe_graphs) == 1          # nothing was committed: the set `last_*` does not alias is always set 0
 
 
+def test_prefetched_front_end_equals_unprefetched(weights, T):
+    """track_camera(..., next_frame=...) queues the next frame's front end on the side stream under this frame's pose solve
+    (three graph sets rotating).  Same kernels on the same inputs: clouds and pyramids bit-identical to the unpipelined
+    tracker, poses equal; a frame that was NOT the prefetched one drops the prefetch."""
+    d = pkg()
+    calib = d.FrameIntrinsic(*T["calib"].tolist())
+    first = d.Isometry(q=d.Quaternion(array=d.synth.FIRST_TQ[3:]), t=np.array(d.synth.FIRST_TQ[:3]))
+    cfg = dict(TRACKING)
+    cfg["iter_config"] = [{"n": 3, "type": [["rgb", 2]]}, {"n": 3, "type": [["sdf"], ["rgb", 1]]}, {"n": 8, "type": [["sdf"], ["rgb", 0]]}]
+    frames = [_frame(T, i % 3) for i in range(9)]
+    order = [0, 1, 2, 1, 0, 1, 2, 1, 2]
+    frames = [frames[i] for i in order]
+    out = {}
+    m = make_map(weights)                                            # ONE map for both runs (its latents are built with float atomics)
+    for pipe in (True, False):
+        trk = d.SDFTracker(m, ns(cfg))
+        res = []
+        for i, (rgb, depth) in enumerate(frames):
+            nxt = frames[i + 1] if (pipe and i + 1 < len(frames)) else None
+            if pipe and i == 5:
+                nxt = frames[0]                                     # announce a frame that does not come: the prefetch is dropped
+            pose = trk.track_camera(rgb, depth, calib, first if i == 0 else None, next_frame=nxt)
+            if i == 0 and pipe:
+                pc, nrm = trk.last_processed_pc
+                m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+            res.append((pose.q.rotation_matrix.copy(), pose.t.copy(), trk.last_processed_pc[0].clone(), trk.last_processed_pc[1].clone(),
+                        [t.clone() for t in trk.last_intensity], [t.clone() for t in trk.last_depth]))
+        out[pipe] = res
+        if pipe:
+            assert len(trk._fe_graphs) == 3                          # last committed / current / prefetched
+    diffs = []
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        for x, y in zip(a[4] + a[5], b[4] + b[5]):
+            assert torch.equal(torch.nan_to_num(x, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
+        diffs.append(max(np.abs(a[0] - b[0]).max(), np.abs(a[1] - b[1]).max()))
+    print("pose differences pipelined vs not:", ["%.1e" % x for x in diffs])
+    # same kernels, same launch geometry, statically dealt photometric chunks: the solve is reproducible up to the order of the
+    # float64 atomics that join the block sums
+    assert max(diffs) < 1e-7, diffs
+
+
 def test_graph_front_end_with_uncommitted_calls(weights, T):
     """A call that commits no pose (for_pc=True) between tracked frames must not make the next frame's photometric term
     read the frame against itself: the graphed front end replays the set `last_*` does not alias.  Same poses as the
@@ -155,8 +200,8 @@ def test_graph_front_end_with_uncommitted_calls(weights, T):
     cfg["iter_config"] = [{"n": 3, "type": [["rgb", 2]]}, {"n": 3, "type": [["sdf"], ["rgb", 1]]}, {"n": 8, "type": [["sdf"], ["rgb", 0]]}]
     plan = [(0, "set"), (1, "track"), (2, "pc"), (2, "track"), (0, "pc"), (1, "pc"), (1, "track"), (2, "pc"), (2, "track")]
     out = {}
+    m = make_map(weights)                 # one map for both runs: its latents come from float atomics, i.e. differ run to run in the last bits
     for graph in (True, False):
-        m = make_map(weights)
         trk = d.SDFTracker(m, ns(cfg))
         trk.graph_frontend = graph
         poses = []
@@ -166,7 +211,7 @@ def test_graph_front_end_with_uncommitted_calls(weights, T):
                 trk.track_camera(rgb, depth, calib, for_pc=True)
                 continue
             pose = trk.track_camera(rgb, depth, calib, first if what == "set" else None)
-            if what == "set":
+            if what == "set" and graph:
                 pc, nrm = trk.last_processed_pc
                 m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
             poses.append((pose.q.rotation_matrix.copy(), pose.t.copy()))

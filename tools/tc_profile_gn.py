@@ -15,7 +15,7 @@ buf = (C.c_ulonglong * 256)(); n = C.c_int(0)
 for i, (d, c) in enumerate(frames):
     if i == 5:
         torch.cuda.synchronize(); raw.dfb_debug_read_prof(buf, C.byref(n))
-        trk.args.iter_config = [{"n": 1, "type": [["sdf"], ["rgb", int(sys.argv[1]) if len(sys.argv) > 1 else 0]]}]
+        trk.args.iter_config = [{"n": 1, "type": [["sdf"], ["rgb", int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 0]]}]
     bench.refresh(dfb, m, trk, i, d, c, calib, first)
 torch.cuda.synchronize(); raw.dfb_debug_read_prof(buf, C.byref(n))
 t = np.array(list(buf)[:n.value], dtype=np.int64)
@@ -27,7 +27,7 @@ names = ["kernel start", "prologue done"] + [f"t0 {x}" for x in per_tile] + [f"t
 t0 = t[0]; prev = t0
 for i, v in enumerate(t[:len(names)]):
     nm = names[i]
-    if "fwd" in nm or "bwd" in nm or "heads" in nm or "lookup" in nm:
+    if ("fwd" in nm or "bwd" in nm or "heads" in nm or "lookup" in nm) and "-v" not in sys.argv:
         prev = v; continue
     print(f"{i:3d} {nm:28s} +{int(v - prev):6d}  @{int(v - t0):7d} cycles"); prev = v
 

@@ -129,6 +129,12 @@ int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, i
 
 /* system.ext.gradient_xy (imgproc.cpp:21, photometric.cu:3-22,79-93). (H,W) -> (H,W,2), NaN border. */
 int dfb_gradient_xy(const float* intensity, int H, int W, float* grad, void* stream);
+/* Image half of the tracker front end in two launches: depth clipping (main.py:56-57; cut = 0 disables it), intensity =
+ * torch.mean(rgb, -1) (tracker.py:84), the 3-level pyramid of tracker.py:42-57 (F.interpolate bilinear align_corners=True for
+ * intensity, nearest for depth) and gradient_xy of every level.  Outputs: I0,D0 [H,W], I1,D1 [H/2,W/2], I2,D2 [H/4,W/4],
+ * G0..G2 [h,w,2].  Bit-identical to the torch CUDA kernels the reference calls (test_frame_images_equals_torch). */
+int dfb_frame_images(const float* rgb, const float* depth, int H, int W, float cut_near, float cut_far, int cut, float* I0, float* D0,
+                     float* I1, float* D1, float* I2, float* D2, float* G0, float* G1, float* G2, void* stream);
 /* system.ext.rgb_odometry (imgproc.cpp:14-20, photometric.cu:24-77,95-138).  f (H,W) and, if J != NULL,
  * J (H,W,6); NaN where invalid.  h_intr = fx,fy,cx,cy; h_krkinv row-major 3x3; h_kt 3. */
 int dfb_rgb_odometry(const float* prev_I, const float* prev_D, const float* cur_I, const float* cur_D,

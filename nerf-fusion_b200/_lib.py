@@ -92,6 +92,7 @@ SIGNATURES = {
     "dfb_preprocess_frame": (_I, [_P, _I, _I, _F, _F, _F, _F, _I, _F, _I, _F, _FP, _F, _I, _P, _P, _P, _P, _SZ, _P]),
     "dfb_groupby_sum": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "dfb_gradient_xy": (_I, [_P, _I, _I, _P, _P]),
+    "dfb_frame_images": (_I, [_P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dfb_rgb_odometry": (_I, [_P, _P, _P, _P, _P, _I, _I, _FP, _FP, _FP, _F, _F, _P, _P, _P]),
     "dfb_rgb_hg": (_I, [_P, _P, _P, _P, _P, _I, _I, _FP, _FP, _FP, _F, _F, _I, _F, _I, _P, _P]),
     "dfb_integrate_ws_bytes": (_SZ, [_I, _I64]),
@@ -123,9 +124,9 @@ SIGNATURES = {
 
 # kernels (and memset nodes excluded) each entry point launches; used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
-    "dfb_ingest_frame": 1, "dfb_transform_points": 1, "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 6,
-    "dfb_point_box_filter": 14, "dfb_preprocess_frame": 45, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
-    "dfb_integrate_plan": 6, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
+    "dfb_ingest_frame": 1, "dfb_transform_points": 1, "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 8, "dfb_estimate_normals": 8, "dfb_scatter_mean": 5,
+    "dfb_point_box_filter": 12, "dfb_preprocess_frame": 38, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_frame_images": 2, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
+    "dfb_integrate_plan": 5, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
     "gn_kernel": 1,                    # launched inside dfb_gauss_newton (count reported through h_stats[7])
     "dfb_latent_adam_step": 2, "dfb_shard_phase1": 2, "dfb_shard_phase2": 3, "dfb_shard_phase3": 2, "dfb_shard_phase4": 3, "dfb_shard_phase5": 4, "dfb_shard_barrier": 1,

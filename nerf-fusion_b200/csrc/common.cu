@@ -83,29 +83,23 @@ __global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const void* in, int n, 
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(SCAN_T) scan_of_sums(int* block_sums, int nb, int* total, const int* __restrict__ n_dev) {
-  __shared__ int tot;
-  if (n_dev) nb = min(nb, (*n_dev + SCAN_TILE - 1) / SCAN_TILE);
-  int carry = 0;
-  for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
-    int i = b0 + threadIdx.x;
-    int v = i < nb ? block_sums[i] : 0;
-    int ex = block_excl_scan(v, &tot);
-    if (i < nb) block_sums[i] = carry + ex;
-    carry += tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    block_sums[nb] = carry;
-    if (total) *total = carry;
-  }
-}
-
+// Second (and last) launch of a scan: every tile adds up the sums of the tiles before it on its own (at most a few
+// thousand values, L2-resident) instead of waiting for a separate single-block scan of the tile sums; the tile holding the
+// last element also writes the total.
 template <bool POPC>
-__global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, int n, const int* block_sums, const int* __restrict__ n_dev) {
-  __shared__ int tot;
+__global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, int n, const int* __restrict__ block_sums, int* __restrict__ total,
+                                                     const int* __restrict__ n_dev) {
+  __shared__ int tot, pre;
   if (n_dev) n = min(n, *n_dev);
+  if (n <= 0) {
+    if (total && blockIdx.x == 0 && threadIdx.x == 0) *total = 0;
+    return;
+  }
   if (blockIdx.x * SCAN_TILE >= n) return;
+  int p = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += SCAN_T) p += block_sums[i];
+  block_excl_scan(p, &pre);
+  __syncthreads();
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
   int v[SCAN_E];
   int s = 0;
@@ -114,7 +108,8 @@ __global__ void __launch_bounds__(SCAN_T) scan_apply(const void* in, int* out, i
     v[e] = scan_load<POPC>(in, base + e, n);
     s += v[e];
   }
-  int ex = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+  int ex = block_excl_scan(s, &tot) + pre;
+  if (total && threadIdx.x == 0 && (blockIdx.x + 1) * SCAN_TILE >= n) *total = pre + tot;
 #pragma unroll
   for (int e = 0; e < SCAN_E; ++e) {
     if (base + e < n) out[base + e] = ex;
@@ -130,8 +125,7 @@ static int scan_impl(const void* in, int* out, int n, int* block_sums, int* tota
   }
   int nb = div_up(n, SCAN_TILE);
   scan_tile_sums<POPC><<<nb, SCAN_T, 0, s>>>(in, n, block_sums, n_dev);
-  scan_of_sums<<<1, SCAN_T, 0, s>>>(block_sums, nb, total, n_dev);
-  scan_apply<POPC><<<nb, SCAN_T, 0, s>>>(in, out, n, block_sums, n_dev);
+  scan_apply<POPC><<<nb, SCAN_T, 0, s>>>(in, out, n, block_sums, total, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

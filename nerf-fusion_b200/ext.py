@@ -120,6 +120,26 @@ def gradient_xy(intensity):
     return g
 
 
+def frame_images(rgb, depth, depth_cut=None):
+    """Image half of the tracker front end (tracker.py:42-57, 84; main.py:56-57) in two launches: depth clipping, intensity =
+    mean over the colour axis, the 3-level pyramid (bilinear align_corners=True / nearest) and gradient_xy of every level.
+    rgb f32[H,W,3], depth f32[H,W] -> (Is, Ds, Gs), three levels each; bit-identical to the torch ops of the reference."""
+    _chk(rgb, "rgb", torch.float32); _chk(depth, "depth", torch.float32)
+    H, W = depth.shape
+    if tuple(rgb.shape) != (H, W, 3):
+        raise RuntimeError("frame_images: rgb must be (H, W, 3)")
+    dev = depth.device
+    dims = [(H, W), (H // 2, W // 2), (H // 2 // 2, W // 2 // 2)]
+    Is = [torch.empty(d, dtype=torch.float32, device=dev) for d in dims]
+    Ds = [torch.empty(d, dtype=torch.float32, device=dev) for d in dims]
+    Gs = [torch.empty(d + (2,), dtype=torch.float32, device=dev) for d in dims]
+    near, far = (float(depth_cut[0]), float(depth_cut[1])) if depth_cut is not None else (0.0, 0.0)
+    with torch.cuda.device(dev):
+        check(_lib.load().dfb_frame_images(_p(rgb), _p(depth), H, W, near, far, int(depth_cut is not None), _p(Is[0]), _p(Ds[0]),
+                                           _p(Is[1]), _p(Ds[1]), _p(Is[2]), _p(Ds[2]), _p(Gs[0]), _p(Gs[1]), _p(Gs[2]), _stream()))
+    return Is, Ds, Gs
+
+
 def rgb_odometry(prev_intensity, prev_depth, cur_intensity, cur_depth, cur_dIdxy, intr, krkinv_data, kt_data,
                  min_grad_scale, max_depth_delta, compute_J):
     """system.ext.rgb_odometry (imgproc.cpp:14-20): returns [f] or [f, J]."""

@@ -70,6 +70,7 @@ class SDFTracker:
         # (same control flow, kept for A/B tests and as executable documentation of tracker.py:225-288)
         self.native_gn = True
         self.fused_preprocess = True       # one C call for tracker.py:89-120 (False: the op-by-op path, same results)
+        self.fused_images = True           # intensity / depth cut / pyramids / gradients in two launches (False: the torch ops, same bits)
         # True: the per-frame front end (intensity, image pyramid, gradients, fused preprocessing: ~55 launches, no host
         # decisions) is captured once per (image size, intrinsics) into a CUDA graph and replayed from static buffers
         self.graph_frontend = True
@@ -95,6 +96,12 @@ class SDFTracker:
         # 700 -> 850 us, frame 1.19 -> 1.13 ms); reserving 16..48 SMs shortens the front end to ~650 us but lengthens the solve
         # more (the long normals blocks still land on the solve's SMs between evaluations): default 0.
         self._reserve_sms = int(os.environ.get("DFB_GN_RESERVE_SMS", "0"))
+        # "after" (default): the next frame's front end is queued the moment this frame's solve has returned, BEFORE the host does
+        # its bookkeeping for the frame (pose algebra, copies of the cloud, a keyframe's integration): the GPU never idles between
+        # frames and nothing competes with the solve for SMs.  "before": queued ahead of the solve, runs beside it (measured: the
+        # two time-slice rather than overlap, see above).
+        self.prefetch_mode = os.environ.get("DFB_PREFETCH", "after")
+        self._pf_deferred = None
         self._solve_stream = None
         self.time_kernels = False          # bench.py: CUDA-event timing of the SDF-term launches inside the C driver
         self.sdf_kernel_us = 0; self.sdf_queries_J = 0; self.sdf_queries_noJ = 0
@@ -142,11 +149,14 @@ class SDFTracker:
         """Everything of tracker.py:75-120 that needs no host decision: intensity, pyramids, gradients, preprocessing
         (and, when depth_cut = (near, far) is given, the caller's depth clipping of main.py:56-57).
         Returns (Is, Ds, Gs, points (n_max,3), normals (n_max,3), count i32[1]); no host sync."""
-        if depth_cut is not None:
-            depth_data = torch.where((depth_data < depth_cut[0]) | (depth_data > depth_cut[1]),
-                                     torch.full_like(depth_data, float("nan")), depth_data)
-        cur_intensity = torch.mean(rgb_data, dim=-1)
-        Is, Ds, Gs = self._make_image_pyramid(cur_intensity, depth_data)
+        if self.fused_images and depth_data.size(0) >= 8 and depth_data.size(1) >= 8:
+            Is, Ds, Gs = ext.frame_images(rgb_data, depth_data, depth_cut)        # 2 launches instead of ~13 torch kernels, same bits
+        else:
+            if depth_cut is not None:
+                depth_data = torch.where((depth_data < depth_cut[0]) | (depth_data > depth_cut[1]),
+                                         torch.full_like(depth_data, float("nan")), depth_data)
+            cur_intensity = torch.mean(rgb_data, dim=-1)
+            Is, Ds, Gs = self._make_image_pyramid(cur_intensity, depth_data)
         # the front end owns its workspace: the captured graphs keep its address (ext.preprocess_frame, `ws`)
         shape = tuple(Ds[0].shape)
         ws = self._fe_ws.get(shape)
@@ -222,6 +232,11 @@ class SDFTracker:
         self._fe_cur[base] = idx
         return self._fe_replay(self._fe_entry(base, idx, rgb_data, depth_data, calib, depth_cut), rgb_data, depth_data)
 
+    def _launch_deferred_prefetch(self):
+        d, self._pf_deferred = self._pf_deferred, None
+        if d is not None:
+            self.prefetch_frame(*d)
+
     @property
     def prefetch_stream(self):
         """The side stream prefetched front ends run on (callers that produce the next frame on the device, e.g. an ingest
@@ -274,8 +289,12 @@ class SDFTracker:
             with torch.cuda.device(self.map.device):
                 cur_intensity, cur_depth, cur_dIdxy, out_p, out_n, cnt = fe(rgb_data.contiguous(), depth_data.contiguous(), calib,
                                                                             depth_cut)
+                self._pf_deferred = None
                 if next_frame is not None and graphed:
-                    self.prefetch_frame(next_frame[0], next_frame[1], calib, depth_cut)
+                    if self.prefetch_mode == "before":
+                        self.prefetch_frame(next_frame[0], next_frame[1], calib, depth_cut)
+                    else:                                         # queued the moment the pose solve has returned (_gauss_newton_native)
+                        self._pf_deferred = (next_frame[0], next_frame[1], calib, depth_cut)
             # The row count stays on the device while the pose solve is queued behind the front end (the kernels read it
             # there); it is read back once the solve has returned.
             defer = self.native_gn and set_pose is None and not for_pc and len(self.all_pd_pose) > 0
@@ -305,6 +324,7 @@ class SDFTracker:
         # (graph outputs are static buffers reused a few frames later: hand out copies)
         self.last_processed_pc = [pc_data.clone(), normal_data.clone()] if graphed else [pc_data, normal_data]
         if for_pc:
+            self._launch_deferred_prefetch()
             return self.last_processed_pc
         if set_pose is not None:
             final_pose = set_pose
@@ -319,6 +339,7 @@ class SDFTracker:
             else:                                      # eager outputs are fresh tensors: no set is aliased any more
                 self._fe_busy.clear()
         self.all_pd_pose.append(final_pose)
+        self._launch_deferred_prefetch()                   # (paths that did not go through the native solve)
         return final_pose
 
     # ------------------------------------------------------------------------------------------ GN terms
@@ -426,6 +447,7 @@ class SDFTracker:
                 m.lib.dfb_set_gn_reserved_sms(0)
                 if solve is not cur:
                     cur.wait_stream(solve)
+            self._launch_deferred_prefetch()
         self.n_sdf_evals += stats[1]; self.n_rgb_evals += stats[2]
         if self.time_kernels:
             self.sdf_kernel_us += stats[4]; self.sdf_queries_J += stats[5]; self.sdf_queries_noJ += stats[6]

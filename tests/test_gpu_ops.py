@@ -272,3 +272,31 @@ def test_latent_adam_step_vs_torch(weights):
     g = (m1 / 0.1).cpu()
     assert (g - g1).abs().max() <= 1e-5 * g1.abs().max()
     assert float(grad.abs().sum()) == 0.0                          # left zero for the next iteration
+
+
+def test_frame_images_equals_torch():
+    """dfb_frame_images (depth clipping, intensity, 3-level pyramid, gradients: two launches) against the torch CUDA kernels
+    the reference calls (tracker.py:42-57, 84; main.py:56-57): bit-identical, also for sizes that do not halve evenly."""
+    d = pkg()
+    F = torch.nn.functional
+    g = torch.Generator(device="cpu").manual_seed(11)
+    for (H, W) in ((480, 640), (240, 320), (479, 641), (62, 90)):
+        rgb = (torch.randint(0, 256, (H, W, 3), generator=g).float() / 255.0).to(DEV)
+        depth = (torch.rand((H, W), generator=g) * 6.0).to(DEV)
+        depth[torch.rand((H, W), generator=g).to(DEV) < 0.1] = float("nan")
+        for cut in (None, (0.5, 5.0)):
+            Is, Ds, Gs = d.ext.frame_images(rgb, depth, cut)
+            dd = depth if cut is None else torch.where((depth < cut[0]) | (depth > cut[1]), torch.full_like(depth, float("nan")), depth)
+            i0 = torch.mean(rgb, dim=-1).view(1, 1, H, W)
+            d0 = dd.view(1, 1, H, W)
+            i1 = F.interpolate(i0, (H // 2, W // 2), mode="bilinear", align_corners=True)
+            d1 = F.interpolate(d0, (H // 2, W // 2), mode="nearest")
+            i2 = F.interpolate(i1, (H // 2 // 2, W // 2 // 2), mode="bilinear", align_corners=True)
+            d2 = F.interpolate(d1, (H // 2 // 2, W // 2 // 2), mode="nearest")
+            ref_I = [t[0, 0].contiguous() for t in (i0, i1, i2)]
+            ref_D = [t[0, 0].contiguous() for t in (d0, d1, d2)]
+            for a, b in zip(Is + Ds, ref_I + ref_D):
+                assert a.shape == b.shape
+                assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)), (H, W, cut)
+            for a, b in zip(Gs, ref_I):
+                assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(d.ext.gradient_xy(b), nan=-1.0))

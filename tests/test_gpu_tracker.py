@@ -161,15 +161,17 @@ def test_prefetched_front_end_equals_unprefetched(weights, T):
     frames = [frames[i] for i in order]
     out = {}
     m = make_map(weights)                                            # ONE map for both runs (its latents are built with float atomics)
-    for pipe in (True, False):
+    for pipe in ("after", "before", False):                          # queued after this frame's solve (default) / ahead of it / never
         trk = d.SDFTracker(m, ns(cfg))
+        if pipe:
+            trk.prefetch_mode = pipe
         res = []
         for i, (rgb, depth) in enumerate(frames):
             nxt = frames[i + 1] if (pipe and i + 1 < len(frames)) else None
             if pipe and i == 5:
                 nxt = frames[0]                                     # announce a frame that does not come: the prefetch is dropped
             pose = trk.track_camera(rgb, depth, calib, first if i == 0 else None, next_frame=nxt)
-            if i == 0 and pipe:
+            if i == 0 and pipe == "after":
                 pc, nrm = trk.last_processed_pc
                 m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
             res.append((pose.q.rotation_matrix.copy(), pose.t.copy(), trk.last_processed_pc[0].clone(), trk.last_processed_pc[1].clone(),
@@ -178,11 +180,12 @@ def test_prefetched_front_end_equals_unprefetched(weights, T):
         if pipe:
             assert len(trk._fe_graphs) == 3                          # last committed / current / prefetched
     diffs = []
-    for a, b in zip(out[True], out[False]):
-        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-        for x, y in zip(a[4] + a[5], b[4] + b[5]):
-            assert torch.equal(torch.nan_to_num(x, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
-        diffs.append(max(np.abs(a[0] - b[0]).max(), np.abs(a[1] - b[1]).max()))
+    for a, a2, b in zip(out["after"], out["before"], out[False]):
+        for a_ in (a, a2):
+            assert torch.equal(a_[2], b[2]) and torch.equal(a_[3], b[3])
+            for x, y in zip(a_[4] + a_[5], b[4] + b[5]):
+                assert torch.equal(torch.nan_to_num(x, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
+            diffs.append(max(np.abs(a_[0] - b[0]).max(), np.abs(a_[1] - b[1]).max()))
     print("pose differences pipelined vs not:", ["%.1e" % x for x in diffs])
     # same kernels, same launch geometry, statically dealt photometric chunks: the solve is reproducible up to the order of the
     # float64 atomics that join the block sums

@@ -52,5 +52,6 @@ def run(pipe):
         print(f"   frame {k}: front end [{fe[k][0] * 1e3:7.0f} .. {fe[k][1] * 1e3:7.0f}]  solve [{so[k][0] * 1e3:7.0f} .. {so[k][1] * 1e3:7.0f}] us")
 
 
-run(False)
-run(True)
+for _ in range(2):
+    run(False)
+    run(True)

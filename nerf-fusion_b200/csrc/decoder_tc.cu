@@ -663,7 +663,11 @@ __global__ void __launch_bounds__(CTA_T, 1) gn_eval_kernel(MapDev M, const float
     const int rem = S.tiles - S.full * S.slots;                     // tiles of the partial round: slots j < rem have one more tile
     const int jslot = c.grp * (int)gridDim.x + (int)blockIdx.x;
     const int rank = jslot >= rem ? jslot - rem : (S.slots - rem) + jslot;
-    for (int ch = rank; ch * (GT * RGB_PIX) < npx; ch += S.slots) {
+    // ... and ONLY to them while that leaves at most 8 chunks (~1/4 of a tile's time) per group: a group that still has a tile
+    // of the partial round to run is the evaluation's critical path
+    const int n_idle = S.slots - rem, n_chunks = (npx + GT * RGB_PIX - 1) / (GT * RGB_PIX);
+    const int deal = n_idle * 8 >= n_chunks ? n_idle : S.slots;
+    for (int ch = rank; ch < n_chunks && rank < deal; ch += deal) {
       const int base = ch * (GT * RGB_PIX);
 #pragma unroll
       for (int e = 0; e < RGB_PIX; ++e) {

@@ -75,7 +75,7 @@ struct Ctx {
   uint32_t mma_bar;   // shared address of the "MMA done" barrier
   uint32_t wbar;      // shared address of the first "weights landed" barrier (each completes once)
   uint32_t phase;     // parity of mma_bar
-  uint32_t mask[4][CW / 32];   // ReLU masks of this thread's columns, per layer
+  uint64_t mask[4];            // ReLU masks of this thread's CW = 64 columns, per layer (bit = column within the thread's part)
   uint32_t xh[8], xl[8];       // this thread's half of the packed network inputs (hi / lo), re-staged for layer 3
 };
 
@@ -175,6 +175,17 @@ __device__ __forceinline__ uint32_t lane_base(const Ctx& c) { return c.tmem + ((
 // (epilogues work in 16-column pieces: 16 accumulator + 16 packed registers in flight keep the kernels spill-free)
 constexpr int EW = 16;               // epilogue piece width (columns)
 constexpr int NPIECE = CW / EW;      // pieces per thread per layer
+static_assert(CW == 64, "one 64-bit ReLU mask per thread and layer");
+// The piece loops are NOT unrolled: at the tracker's size a CTA runs 2-3 tiles, i.e. every instruction of the kernel is
+// fetched cold once per CTA, and with the pieces unrolled (12.4 k instructions, ~200 KB) ncu attributed 3.7 of 13.5 warp-cycles
+// per issued instruction to instruction fetch (stall "no_instruction").
+#ifndef DFB_EPI_UNROLL
+#define DFB_PIECE_LOOP _Pragma("unroll 1")
+#else
+#define DFB_PIECE_LOOP _Pragma("unroll")
+#endif
+__device__ __forceinline__ void mask_put(uint64_t& mk, int q, uint32_t m) { mk = (q == 0 ? 0ull : mk) | ((uint64_t)m << (16 * q)); }
+__device__ __forceinline__ uint32_t mask_get(uint64_t mk, int q) { return (uint32_t)(mk >> (16 * q)) & 0xffffu; }
 __device__ __forceinline__ void store_a16(const Ctx& c, int k0, const float* h) {
   uint32_t hi[8], lo[8];
 #pragma unroll
@@ -196,7 +207,7 @@ template <int NCOLS>
 __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const uint32_t tb = lane_base(c) + TM_D;
-#pragma unroll
+  DFB_PIECE_LOOP
   for (int q = 0; q < NPIECE; ++q) {
     const int cb = CW * c.part + EW * q;
     if (cb < NCOLS) {                       // warp-uniform
@@ -211,7 +222,7 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
         m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
         v[4 * i4] = fmaxf(a0, 0.f); v[4 * i4 + 1] = fmaxf(a1, 0.f); v[4 * i4 + 2] = fmaxf(a2, 0.f); v[4 * i4 + 3] = fmaxf(a3, 0.f);
       }
-      if (q & 1) c.mask[layer][q >> 1] |= m << 16; else c.mask[layer][q >> 1] = m;
+      mask_put(c.mask[layer], q, m);
       store_a16(c, cb, v);
     }
   }
@@ -221,13 +232,13 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
 template <int NCOLS>
 __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
   const uint32_t tb = lane_base(c) + TM_D;
-#pragma unroll
+  DFB_PIECE_LOOP
   for (int q = 0; q < NPIECE; ++q) {
     const int cb = CW * c.part + EW * q;
     if (cb < NCOLS) {
       float v[EW];
       tmem_ld16(tb + cb, v);
-      const uint32_t m = c.mask[layer][q >> 1] >> (16 * (q & 1));
+      const uint32_t m = mask_get(c.mask[layer], q);
 #pragma unroll
       for (int i = 0; i < EW; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
       store_a16(c, cb, v);
@@ -288,7 +299,7 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
   const uint32_t tb = lane_base(c) + TM_D;
   float zu[2] = {0.f, 0.f};
   float z1 = 0.f, u1 = 0.f;
-#pragma unroll
+  DFB_PIECE_LOOP
   for (int q = 0; q < NPIECE; ++q) {
     const int cb = CW * c.part + EW * q;
     float v[EW];
@@ -306,7 +317,7 @@ __device__ __forceinline__ void forward(Ctx& c, float& z, float& u) {
       zu[0] = fmaf(wz.x, h0, zu[0]); z1 = fmaf(wz.y, h1, z1); zu[0] = fmaf(wz.z, h2, zu[0]); z1 = fmaf(wz.w, h3, z1);
       zu[1] = fmaf(wv.x, h0, zu[1]); u1 = fmaf(wv.y, h1, u1); zu[1] = fmaf(wv.z, h2, zu[1]); u1 = fmaf(wv.w, h3, u1);
     }
-    if (q & 1) c.mask[3][q >> 1] |= m << 16; else c.mask[3][q >> 1] = m;
+    mask_put(c.mask[3], q, m);
   }
   zu[0] += z1; zu[1] += u1;
   exchange(c, zu, 2);
@@ -321,11 +332,11 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
   const float* sm = reinterpret_cast<const float*>(c.sm + SM_SMALL);
   const uint32_t tb = lane_base(c) + TM_D;
   float ga[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+  DFB_PIECE_LOOP
   for (int q = 0; q < NPIECE; ++q) {                                 // delta3 = (seed_z w4 + seed_u wu) * [a3 > 0]
     const int cb = CW * c.part + EW * q;
     float d[EW];
-    const uint32_t m = c.mask[3][q >> 1] >> (16 * (q & 1));
+    const uint32_t m = mask_get(c.mask[3], q);
     const float4* w4 = reinterpret_cast<const float4*>(sm + DS_W4 + cb);
     const float4* wu = reinterpret_cast<const float4*>(sm + DS_WU + cb);
 #pragma unroll
@@ -353,12 +364,12 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
   epi_bwd<128>(c, 1);
   TC_LAYER((issue3<8, 128, true, 128>(c, 0, IMG_W1H, IMG_W1L)));   // delta0 = delta1 * W1 (masked below)
   float gb[3] = {0.f, 0.f, 0.f};                                   // second set of accumulators: two dependent FMA chains per output
-#pragma unroll
+  DFB_PIECE_LOOP
   for (int q = 0; q < NPIECE; ++q) {
     const int cb = CW * c.part + EW * q;
     float v[EW];
     tmem_ld16(tb + cb, v);
-    const uint32_t m = c.mask[0][q >> 1] >> (16 * (q & 1));
+    const uint32_t m = mask_get(c.mask[0], q);
     const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * cb);
 #pragma unroll
     for (int i4 = 0; i4 < EW / 4; ++i4) {

@@ -68,10 +68,14 @@ def test_config1_preprocessing_and_map(runs):
 
 def test_config1_poses(runs):
     ref, ours, onref, seq = runs["ref"], runs["ours"], runs["onref"], runs["seq"]
+    # Bounds = the reference's own run-to-run floor (two runs of the UNMODIFIED reference on identical inputs: median 1.3e-5,
+    # worst frame 1.5e-4 m, profiles/r02_config1_parity.json), with headroom for its tail: over the GPU runs of round 2 the medians
+    # of these comparisons ranged from 8e-6 to 5e-5 (the operator-level drop-in below, whose arithmetic did not change between
+    # those runs, included), because WHICH iteration ends a group (tracker.py:269) flips on the last bits of the energy.
     dt = _summary("end to end", C1.compare(ours, ref))
-    assert np.median(dt) < 3e-5 and dt.max() < 2e-3
+    assert np.median(dt) < 1e-4 and dt.max() < 2e-3
     dt2 = _summary("fed the reference's points", C1.compare(onref, ref))
-    assert np.median(dt2) < 1.5e-5 and dt2.max() < 2e-3
+    assert np.median(dt2) < 5e-5 and dt2.max() < 2e-3
     gt = max(float(np.abs(p[1] - seq.poses[i][1]).max()) for i, p in enumerate(ours["poses"]))
     gt_ref = max(float(np.abs(p[1] - seq.poses[i][1]).max()) for i, p in enumerate(ref["poses"]))
     print(f"max |t - ground truth|: ours {gt:.2e} m, reference {gt_ref:.2e} m")
@@ -127,10 +131,10 @@ def test_operator_level_dropin(runs):
     cmp_ = C1.compare(drop, ref)
     dt = _summary("reference python on dfb ops vs on its own ops", cmp_)
     assert len(np.setxor1d(drop["map"]["pos"], ref["map"]["pos"])) <= 2 and cmp_["count_equal_frac"] >= 0.99
-    assert np.median(dt) < 3e-5 and dt.max() < 2e-3
+    assert np.median(dt) < 1e-4 and dt.max() < 2e-3                  # (bounds: see test_config1_poses)
     # the class-level path and the operator-level path agree with each other as well
     dt2 = _summary("class-level path vs operator-level drop-in", C1.compare(runs["ours"], drop))
-    assert np.median(dt2) < 3e-5 and dt2.max() < 2e-3
+    assert np.median(dt2) < 1e-4 and dt2.max() < 2e-3
 
 
 def test_extract_mesh_twice_matches_reference(runs):

@@ -17,12 +17,17 @@ if [[ "$what" == *bench* ]]; then
   echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 fi
 if [[ "$what" == *ncu* ]]; then
-  CMD="python bench.py --steps 2 --warmup 3"
-  timeout 600 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base mangled -k regex:3dfb -s ${NCU_SKIP:-300} -c ${NCU_COUNT:-1200} \
+  # launch list of EXACTLY the timed region of the resident pass (cudaProfilerStart/Stop around it), every kernel that runs
+  # there (ours, ATen, memsets are not kernels); then one full capture of $NCU_KERNEL
+  CMD="python bench.py --steps ${NCU_STEPS:-20} --warmup 3"
+  BENCH_PROFILE_REGION=1 timeout 600 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
+  BENCH_PROFILE_REGION=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 6000 \
       --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-sdf_hg_kernel} -s 30 -c 2 \
-      -f -o gpurun_out/prof_${NCU_KERNEL:-sdf_hg_kernel} $CMD > gpurun_out/ncu_full.log 2>&1
-  echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+  python tools/launch_summary.py gpurun_out/launches.csv > gpurun_out/launches.txt 2>&1; head -12 gpurun_out/launches.txt
+  for K in ${NCU_KERNEL:-gn_eval_kernel}; do
+    BENCH_PROFILE_REGION=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$K -s 4 -c 2 \
+        -f -o gpurun_out/prof_$K $CMD > gpurun_out/ncu_full_$K.log 2>&1
+    echo "ncu full $K rc=$?"; tail -2 gpurun_out/ncu_full_$K.log
+  done
 fi

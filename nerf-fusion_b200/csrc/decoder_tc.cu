@@ -92,7 +92,13 @@ template <int KSTEPS, int N, bool BWD, int B_ROWS, int B_S0 = 0>
 __device__ __forceinline__ void issue(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool accumulate_first) {
   constexpr uint32_t idesc = (1u << 4) | ((BWD ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
   const uint64_t bd0 = BWD ? smem_desc(b_addr, (uint32_t)B_ROWS * 128u, 1024) : smem_desc(b_addr, 16, 1024);
+  // (a rolled loop: with the k-steps unrolled the 144 MMAs of an evaluation were 1.6 k instructions -- immediates for every
+  // descriptor -- that only the issuing thread runs, cold, on the critical path of every layer)
+#ifndef DFB_ISSUE_UNROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int s = 0; s < KSTEPS; ++s) {
     const int sb = s + B_S0;
     const uint64_t bd = bd0 + (uint64_t)((BWD ? sb * 2048 : (sb >> 2) * (B_ROWS * 128) + (sb & 3) * 32) >> 4);

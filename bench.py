@@ -49,9 +49,10 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
     capture of this same command (profiles/); None when absent."""
     import csv
-    f = ROOT / "profiles" / "r01_gn_eval_ncu_raw.csv"
-    if not f.exists():
+    cands = sorted((ROOT / "profiles").glob("r*_gn_eval*_ncu_raw.csv"))      # the latest round's capture
+    if not cands:
         return None
+    f = cands[-1]
     try:
         rows = list(csv.reader(open(f)))
         hdr, units, row = rows[0], rows[1], rows[2]

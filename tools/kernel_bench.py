@@ -131,7 +131,7 @@ for eng in (0, 1):
     add(f"integrate_keyframe ({Pw.shape[0]} pts, repeated on the same map) [{'tcgen05' if eng else 'fp32'} encoder]",
         ti, nbytes=Pw.shape[0] * 370, units=(Pw.shape[0], "points"))
 lib.dfb_set_encoder_engine(1)
-out = ROOT / "profiles" / "r01_kernel_table.md"
+out = ROOT / (sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/kernel_table.md")     # copied to profiles/rNN_kernel_table.md
 keys = ["kernel", "time_us", "bound", "TFLOP/s", "GB/s", "frac", "units/s", "note"]
 with open(out, "w") as f:
     f.write(f"# Per-kernel micro-benchmarks (1x B200, CUDA events, median; peaks: HBM {PK['hbm_gbs']} GB/s, bf16 burst {PK['bf16_tflops']} TFLOP/s, measured)\n\n")

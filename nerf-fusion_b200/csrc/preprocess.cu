@@ -213,7 +213,9 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restri
   if (i >= n) return;
   float4 p = reinterpret_cast<const float4*>(pc4)[i];
   int c = cell_of[i];
-  int pos = cell_start[c] + atomicAdd(&cursor[c], 1);
+  // `cursor` IS the cell-count array: counting it back down to zero hands out the slots of the cell (in reverse) and leaves the
+  // array cleared for the next grid -- no zeroing pass between the count and the scatter
+  int pos = cell_start[c] + atomicSub(&cursor[c], 1) - 1;
   sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
 }
 
@@ -551,7 +553,6 @@ static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, c
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s, &w.gp->ncell1);
   if (rc) return rc;
-  zero_words_dev(w.cell_count, cap + 1, &w.gp->ncell1, s);
   grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted, n_dev);
   DFB_LAUNCH_CHECK();
   return DFB_OK;

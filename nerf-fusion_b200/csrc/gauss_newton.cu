@@ -179,12 +179,25 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
   };
 
   int rc = DFB_OK;
+  // A look-ahead launch that was queued behind the evaluation that ended its group returns at once on the device; its record
+  // is drained only AFTER the next group's first evaluation has been enqueued, so the GPU goes from one group to the next
+  // without waiting for a host round trip (ring: at most the skipped slot + two slots of the next group are outstanding).
+  Slot skipped; bool have_skipped = false;
+  auto drain_skipped = [&]() -> int {
+    if (!have_skipped) return DFB_OK;
+    have_skipped = false;
+    Rec r;
+    int rc2 = wait(skipped, r);
+    if (rc2 == DFB_OK) account(skipped, r);
+    return rc2;
+  };
   for (int gi = 0; gi < h_cfg->n_groups && rc == DFB_OK && !error; ++gi) {
     const int n_it = h_cfg->n_iter[gi];
     DFB_CHECK_ARG(n_it >= 0 && n_it < 100000, "gauss_newton: n_iter out of range");
     if (h_cfg->rgb_level[gi] >= 0) DFB_CHECK_ARG(h_levels && h_intr && h_cfg->rgb_level[gi] < 3, "gauss_newton: rgb term needs pyramid levels and intrinsics");
     Slot cur, next;
     rc = enqueue(gi, 0, cur);
+    if (rc == DFB_OK) rc = drain_skipped();
     bool have_next = false;
     for (int step = 0; rc == DFB_OK; ++step) {
       have_next = false;
@@ -199,15 +212,13 @@ extern "C" int dfb_gauss_newton(const dfb_map_params* h_params, const dfb_gn_con
       account(cur, r);
       const bool group_over = r.broke || r.error || step == n_it;
       if (group_over) {
-        if (have_next) {                                            // already queued: it returns at once on the device; drain its record
-          rc = wait(next, r);
-          if (rc == DFB_OK) account(next, r);
-        }
+        if (have_next) { skipped = next; have_skipped = true; }     // already queued: it returns at once on the device
         break;
       }
       cur = next;
     }
   }
+  if (rc == DFB_OK) rc = drain_skipped();
   if (rc) { cudaStreamSynchronize(s); return rc; }
   if (error) { dfb::set_error("gauss_newton: singular normal equations"); h_stats[3] = 1; return DFB_E_INVALID; }
   memcpy(h_delta_pose, delta_out, sizeof(double) * 12);

@@ -228,7 +228,7 @@ __device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, f
 __global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restrict__ sorted, int n,
                                                            const GridParams* gpp, const int* __restrict__ cell_start,
                                                            int nb_points, float radius, uint8_t* __restrict__ mask,
-                                                           const int* __restrict__ n_dev) {
+                                                           const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
   if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restr
     }
   }
   mask[__float_as_int(q.w)] = count >= nb_points ? 1 : 0;
+  if (flag) flag[__float_as_int(q.w)] = count >= nb_points ? 1 : 0;     // fused path: the compaction's scan input, no separate pass
 }
 
 // pcproc.cu:21-96, same expression shapes (including the double-precision promotions through M_PI).
@@ -294,7 +295,7 @@ __device__ float4 sym3eig_smallest(float3 x1, float3 x2, float3 x3) {
 // pcproc.cu:107-158 on the sorted key list (slot 0 = the query itself): mean, covariance, smallest eigenvector, orientation
 template <int K>
 __device__ __forceinline__ void normal_from_keys(const unsigned long long (&key)[K], const float4 q, const float4* __restrict__ pc4, int max_nn,
-                                                 float r2, float3 cam, float* __restrict__ normals) {
+                                                 float r2, float3 cam, float* __restrict__ normals, int* __restrict__ flag = nullptr) {
   int oi = __float_as_int(q.w);
   float3 mean = make_float3(0.f, 0.f, 0.f);
   float valid = 0.f;
@@ -308,6 +309,7 @@ __device__ __forceinline__ void normal_from_keys(const unsigned long long (&key)
   }
   if (valid < 5.0f) {
     normals[3 * oi + 0] = normals[3 * oi + 1] = normals[3 * oi + 2] = CUDART_NAN_F;
+    if (flag) flag[oi] = 0;
     return;
   }
   mean.x /= valid; mean.y /= valid; mean.z /= valid;
@@ -329,6 +331,7 @@ __device__ __forceinline__ void normal_from_keys(const unsigned long long (&key)
   normals[3 * oi + 0] = nrm.x;
   normals[3 * oi + 1] = nrm.y;
   normals[3 * oi + 2] = nrm.z;
+  if (flag) flag[oi] = isnan(nrm.x) ? 0 : 1;       // what flag_from_normals_kernel computed in a pass of its own
 }
 
 // Position of a query inside its grid cell (in cell units) and the distance, in cells, from the query to the slab of cells
@@ -353,7 +356,7 @@ __device__ __forceinline__ float cell_gap(int d, float frac) {
 template <int K>
 __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
                                                          const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
-                                                         float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
+                                                         float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
   if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
     const float reach = (float)R * g.cell * 0.9999f;
     if (__uint_as_float((unsigned)(key[last] >> 32)) < reach * reach) break;
   }
-  normal_from_keys<K>(key, q, pc4, max_nn, r2, cam, normals);
+  normal_from_keys<K>(key, q, pc4, max_nn, r2, cam, normals, flag);
 }
 
 
@@ -474,7 +477,7 @@ __device__ __forceinline__ void nb_merge(unsigned long long (&top)[16], const un
 
 __global__ void __launch_bounds__(NB_T, 4) normals_batched_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
                                                                   const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
-                                                                  float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev) {
+                                                                  float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
   __shared__ unsigned long long s_batch[NB_CAP * NB_T];
   if (n_dev) n = *n_dev;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -536,15 +539,21 @@ __global__ void __launch_bounds__(NB_T, 4) normals_batched_kernel(const float4* 
     if (__uint_as_float((unsigned)(top[last] >> 32)) < reach * reach) done = true;
     if (__all_sync(0xffffffffu, done)) break;
   }
-  if (live) normal_from_keys<16>(top, q, pc4, max_nn, r2, cam, normals);
+  if (live) normal_from_keys<16>(top, q, pc4, max_nn, r2, cam, normals, flag);
 }
 
 static bool normals_use_v1() { static const bool v = getenv("DFB_NORMALS_V1") != nullptr; return v; }   // A/B switch: one thread per query, immediate insertion
 
 // cell: target cell edge (grown by 1.25x steps until the bounding box fits into `cap` cells)
+__device__ __forceinline__ void bbox_init_inline(unsigned* bbox) {   // bbox_init_kernel's work, by threads 0..6 of a caller's block 0
+  const int t = threadIdx.x;
+  if (t < 3) bbox[t] = 0xffffffffu;
+  else if (t < 6) bbox[t] = 0u;
+  else if (t == 6) { bbox[7] = bbox[6]; bbox[6] = 0u; }
+}
 static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, cudaStream_t s, const int* n_dev = nullptr,
-                      const int* hint_n = nullptr, float cell_max = 0.f) {
-  bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);
+                      const int* hint_n = nullptr, float cell_max = 0.f, bool bbox_ready = false) {
+  if (!bbox_ready) bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);     // (the fused path has the preceding compaction kernel do it)
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
   grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp, hint_n, cell_max);
   // counts, scan and cursor reset cover the ncell + 1 cells the bounding box needs (device-side length), not the capacity
@@ -690,7 +699,10 @@ __global__ void __launch_bounds__(256) box_key_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) box_rank_kernel(const long long* __restrict__ keys, int n,
                                                        const uint32_t* __restrict__ bits, const int* __restrict__ word_rank,
-                                                       const BoxParams* bpp, int* rank_out, const int* __restrict__ n_dev) {
+                                                       const BoxParams* bpp, int* rank_out, const int* __restrict__ n_dev, int32_t* n_out) {
+  // (key range beyond the bitmap capacity: the row count becomes -1 here, before the segmented mean reads it, so that pass does
+  // nothing and the host raises; this was a one-thread kernel of its own)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bpp->overflow) *n_out = -1;
   if (n_dev) n = *n_dev;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -700,9 +712,6 @@ __global__ void __launch_bounds__(256) box_rank_kernel(const long long* __restri
   rank_out[i] = word_rank[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
 }
 
-__global__ void box_finish_kernel(const BoxParams* bpp, int32_t* n_out) {
-  if (bpp->overflow) *n_out = -1;
-}
 
 // ------------------------------------------------------------------------------------------------
 // groupby_sum (indexing.cu:59-71): one thread per element, coalesced reads, one red per element
@@ -734,30 +743,18 @@ __global__ void __launch_bounds__(256) unproject_sub_kernel(const float* __restr
 
 // order-preserving compaction (the reference's boolean-mask indexing keeps row order, tracker.py:104-116)
 __global__ void __launch_bounds__(256) compact4_kernel(const float* __restrict__ in4, const int* __restrict__ flag, const int* __restrict__ pos,
-                                                       int n, const int* __restrict__ n_dev, float* __restrict__ out4) {
+                                                       int n, const int* __restrict__ n_dev, float* __restrict__ out4, unsigned* init_bbox = nullptr) {
+  if (init_bbox && blockIdx.x == 0) bbox_init_inline(init_bbox);     // for the grid build that follows
   if (n_dev) n = *n_dev;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !flag[i]) return;
   reinterpret_cast<float4*>(out4)[pos[i]] = reinterpret_cast<const float4*>(in4)[i];
 }
 
-__global__ void __launch_bounds__(256) flag_from_mask_kernel(const uint8_t* __restrict__ mask, int n_max, const int* __restrict__ n_dev,
-                                                             int* __restrict__ flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_max) return;
-  flag[i] = (i < *n_dev && mask[i]) ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256) flag_from_normals_kernel(const float* __restrict__ nrm, int n_max, const int* __restrict__ n_dev,
-                                                                int* __restrict__ flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_max) return;
-  flag[i] = (i < *n_dev && !isnan(nrm[3 * (size_t)i])) ? 1 : 0;
-}
-
 __global__ void __launch_bounds__(256) compact_pn_kernel(const float* __restrict__ pc4, const float* __restrict__ nrm, const int* __restrict__ flag,
                                                          const int* __restrict__ pos, int n, const int* __restrict__ n_dev,
-                                                         float* __restrict__ p3, float* __restrict__ n3) {
+                                                         float* __restrict__ p3, float* __restrict__ n3, unsigned* init_bbox = nullptr) {
+  if (init_bbox && blockIdx.x == 0) bbox_init_inline(init_bbox);     // for the box filter's bounding box
   if (n_dev) n = *n_dev;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !flag[i]) return;
@@ -901,8 +898,8 @@ size_t dfb_box_filter_ws_bytes(int n) {
 }
 
 static int box_filter_impl(const float* points, const float* normals, int n, const int* n_dev, float voxel_size, int div_mode,
-                           float* out_points, float* out_normals, int32_t* d_n_out, Arena& a, cudaStream_t s) {
-  unsigned* bbox = a.take<unsigned>(8);
+                           float* out_points, float* out_normals, int32_t* d_n_out, Arena& a, cudaStream_t s, unsigned* ready_bbox = nullptr) {
+  unsigned* bbox = ready_bbox ? ready_bbox : a.take<unsigned>(8);
   BoxParams* bp = a.take<BoxParams>(1);
   long long* keys = a.take<long long>(n + 1);
   const int max_words = (int)(BOX_BITS_CAP / 32);
@@ -911,7 +908,7 @@ static int box_filter_impl(const float* points, const float* normals, int n, con
   int* bsums = a.take<int>(max_words / 2048 + 8);
   int* rank = a.take<int>(n + 1);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
+  if (!ready_bbox) bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(points, n, 3, bbox, n_dev);
   box_params_kernel<<<1, 1, 0, s>>>(bbox, voxel_size, div_mode, bp);
   zero_words_dev(bits, max_words + 1, &bp->n_zero, s);        // only the words this frame's bounding box uses
@@ -919,13 +916,10 @@ static int box_filter_impl(const float* points, const float* normals, int n, con
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_popc(bits, word_rank, max_words, bsums, d_n_out, s, &bp->n_words);
   if (rc) return rc;
-  box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank, n_dev);
+  box_rank_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, bits, word_rank, bp, rank, n_dev, d_n_out);
   DFB_LAUNCH_CHECK();
   rc = segmented_mean(points, normals, nullptr, rank, n, 3, n, d_n_out, out_points, out_normals, a, s, n_dev);
-  if (rc) return rc;
-  box_finish_kernel<<<1, 1, 0, s>>>(bp, d_n_out);
-  DFB_LAUNCH_CHECK();
-  return DFB_OK;
+  return rc;
 }
 
 int dfb_point_box_filter(const float* points, const float* normals, int n, float voxel_size, int div_mode,
@@ -979,35 +973,35 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   DFB_LAUNCH_CHECK();
   int rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[0], s);
   if (rc) return rc;
-  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB);
-  // P2: radius outlier filter
-  rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0]);
+  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB, w.bbox);
+  // P2: radius outlier filter (the kernel writes the compaction flags itself; rows past the device-side count are not scanned)
+  rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0], nullptr, 0.f, true);
   if (rc) return rc;
-  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0]);
-  flag_from_mask_kernel<<<div_up(n, 256), 256, 0, s>>>(mask, n, &counts[0], flag);
+  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0], flag);
   DFB_LAUNCH_CHECK();
-  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[1], s);
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[1], s, &counts[0]);
   if (rc) return rc;
-  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC);
+  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC, w.bbox);
   // P3: normals
   // (cell size from the density the radius filter's grid just measured: grid_params_kernel)
-  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1], &counts[0], normal_radius * 0.5f);
+  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1], &counts[0], normal_radius * 0.5f, true);
   if (rc) return rc;
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   if (max_nn <= 16 && !normals_use_v1())
-    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
   else if (max_nn <= 16)
-    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
   else
-    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1]);
-  flag_from_normals_kernel<<<div_up(n, 256), 256, 0, s>>>(nrmC, n, &counts[1], flag);
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
   DFB_LAUNCH_CHECK();
-  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s);
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s, &counts[1]);
   if (rc) return rc;
-  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcC, nrmC, flag, pos, n, &counts[1], pD, nD);
+  unsigned* box_bbox = a.take<unsigned>(8);
+  if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcC, nrmC, flag, pos, n, &counts[1], pD, nD, box_bbox);
   DFB_LAUNCH_CHECK();
   // P4: box filter
-  return box_filter_impl(pD, nD, n, &counts[2], box_voxel, div_mode, out_points, out_normals, d_n_out, a, s);
+  return box_filter_impl(pD, nD, n, &counts[2], box_voxel, div_mode, out_points, out_normals, d_n_out, a, s, box_bbox);
 }
 
 int dfb_groupby_sum(const float* values, const int64_t* indices, int n, int L, int C, float* sum, int32_t* count,

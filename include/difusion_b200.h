@@ -166,7 +166,9 @@ typedef struct {
 /* Persistent per-map scratch (all-zero between calls; the kernels restore the zeros they disturb):
  *   grid_count  int32[G]            per-cell point counter
  *   grid_bits   uint32[ceil(G/32)]  allocation bitmap
- *   acc         float[cap*29], acc_n int32[cap], touched int32[cap]   per-slot encoder accumulators        */
+ *   acc         int64[cap*29], acc_n int32[cap], touched int32[cap]   per-slot encoder accumulators: 64-bit FIXED-POINT sums in
+ *               units of 2^-34 (integer adds commute: the scatter-add of map.py:446-449 gives the same bits for any order of the
+ *               atomics and any sharding of the samples, unlike the float atomics of indexing.cu:59-71)                       */
 size_t dfb_integrate_ws_bytes(int n, int64_t n_cells);
 
 /* Phase A (map.py:367-388 up to the allocation count): voxel ids, count-prune (unq_mask, the function's return
@@ -184,7 +186,7 @@ int dfb_integrate_plan(const dfb_map_params* h_params, const float* xyz, const f
 int dfb_integrate_commit(const dfb_map_params* h_params, const float* normal, const uint8_t* unq_mask, int n,
                          int64_t* indexer, float* latent_vecs, int64_t* latent_vecs_pos, float* voxel_obs_count,
                          uint8_t* updated_flag, int64_t n_occupied, int64_t capacity, int32_t n_new, uint32_t* grid_bits,
-                         float* acc, int32_t* acc_n, int32_t* touched, const float* encoder_blob, int32_t* d_stats,
+                         int64_t* acc, int32_t* acc_n, int32_t* touched, const float* encoder_blob, int32_t* d_stats,
                          void* ws, size_t ws_bytes, void* stream);
 
 /* network encoder forward on explicit inputs (map.py:446-447 -> di_encoder.py:26-30): x (m,6) -> (m,29). */
@@ -302,7 +304,7 @@ typedef struct {
   int32_t capacity;
   uint32_t* cand_bits;         /* ceil(nx ny nz / 32) words: candidate voxels (allocated, obs_count < encoder_count_th), all ranks' */
   int32_t* grid_count;         /* dfb_shard_local_cells() ints, zero between keyframes */
-  float* acc;                  /* (capacity, 29) zero between keyframes */
+  int64_t* acc;                /* (capacity, 29) fixed-point sums (2^-34 units), zero between keyframes */
   int32_t* acc_n;              /* (capacity,) zero between keyframes */
   int32_t* touched;            /* (capacity,) scratch */
   int32_t* counters;           /* dfb_shard_counter_ints() ints, zero-initialised once; [3*8+3] = n_occupied */

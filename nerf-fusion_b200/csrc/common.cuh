@@ -142,6 +142,17 @@ __device__ __forceinline__ void block_reduce_atomic(const float* vals, double* o
 }
 
 // Accumulate sum w J J^T (upper triangle, 21), sum w r J (6), sum w r^2, count into acc[29].
+// Per-voxel encoder accumulators (I6, map.py:446-449) are 64-bit FIXED-POINT sums (units of 2^-34): integer addition is
+// associative, so the scatter-add gives the same bits whatever order the atomics land in -- run to run, and for any sharding of
+// the samples over GPUs -- where float atomics (the reference's scatter, indexing.cu:59-71) leave the map different in its last
+// bits every run.  One addend is rounded to 5.8e-11 absolute (its FP32 ulp is larger from |v| = 2^-10 up); the sum itself is
+// exact, i.e. more accurate than a float running sum; range +-5e8.
+constexpr float DFB_ACC_SCALE = 17179869184.0f;             // 2^34
+__device__ __forceinline__ void acc_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * DFB_ACC_SCALE));
+}
+__device__ __forceinline__ float acc_read(long long v) { return __double2float_rn((double)v * (1.0 / 17179869184.0)); }
+
 __device__ __forceinline__ void hg_accumulate(float* acc, const float* J, float r, float w, bool with_J) {
   if (with_J) {
     int t = 0;

@@ -246,11 +246,13 @@ __global__ void __launch_bounds__(CTA_T, 2) encoder_kernel(const Sample* __restr
     float o[16];
     encode_tile(c, in, o);
     if (valid && slot >= 0) {
-      float* dst = out + (size_t)(SCATTER ? slot : i) * DFB_LATENT_DIM + 16 * c.part;
+      // SCATTER: `out` is the map's fixed-point accumulator array (common.cuh acc_add: order-independent sums)
+      float* dst = out + (size_t)i * DFB_LATENT_DIM + 16 * c.part;
+      long long* adst = reinterpret_cast<long long*>(out) + (size_t)slot * DFB_LATENT_DIM + 16 * c.part;
 #pragma unroll
       for (int l = 0; l < 16; ++l) {
         if (16 * c.part + l < DFB_LATENT_DIM) {
-          if (SCATTER) atomicAdd(dst + l, o[l]); else dst[l] = o[l];
+          if (SCATTER) acc_add(adst + l, o[l]); else dst[l] = o[l];
         }
       }
     }
@@ -267,21 +269,21 @@ __global__ void __launch_bounds__(CTA_T, 2) encoder_kernel(const Sample* __restr
 
 static int enc_grid(long long m) { return (int)std::min<long long>(div_up(m, etc::T), 2LL * sm_count()); }
 
-int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, float* acc, cudaStream_t s) {
+int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, long long* acc, cudaStream_t s) {
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
   etc::encoder_kernel<true><<<enc_grid(m_max), etc::CTA_T, etc::SM_ALLOC, s>>>(reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, m_dev,
-                                                                            nullptr, 0, 0, tc_blob, acc);
+                                                                            nullptr, 0, 0, tc_blob, reinterpret_cast<float*>(acc));
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
 
 // sharded map: the samples are the segments of the exchange's receive buffer (sharded.cu)
-int tc_encoder_scatter_segments(const void* samples, const int* seg_counts, int n_seg, int seg_cap, const void* tc_blob, float* acc,
+int tc_encoder_scatter_segments(const void* samples, const int* seg_counts, int n_seg, int seg_cap, const void* tc_blob, long long* acc,
                                 cudaStream_t s) {
   if (n_seg < 1 || n_seg > etc::MAX_SEG) { set_error("encoder: 1..%d segments", etc::MAX_SEG); return DFB_E_INVALID; }
   DFB_CUDA(cudaFuncSetAttribute(etc::encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, etc::SM_ALLOC));
   etc::encoder_kernel<true><<<enc_grid((long long)n_seg * seg_cap), etc::CTA_T, etc::SM_ALLOC, s>>>(
-      reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, nullptr, seg_counts, n_seg, seg_cap, tc_blob, acc);
+      reinterpret_cast<const etc::Sample*>(samples), nullptr, 0, nullptr, seg_counts, n_seg, seg_cap, tc_blob, reinterpret_cast<float*>(acc));
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

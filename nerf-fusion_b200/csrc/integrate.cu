@@ -274,7 +274,7 @@ __device__ __forceinline__ void encoder_load(EncSmem& S, const float* __restrict
 
 // samples -> encoder -> scatter-add into acc (map.py:446-449 + indexing.cu:59-71)
 __global__ void __launch_bounds__(ENC_T, 1) encoder_scatter_kernel(const Sample* __restrict__ samples, const int* __restrict__ counters,
-                                                                   const float* __restrict__ blob, float* __restrict__ acc) {
+                                                                   const float* __restrict__ blob, long long* __restrict__ acc) {
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   encoder_load(S, blob);
   const int m = counters[0];
@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(ENC_T, 1) encoder_scatter_kernel(const Sample*
     const float in[6] = {sm.rel[0], sm.rel[1], sm.rel[2], sm.nrm[0], sm.nrm[1], sm.nrm[2]};
     float out[32];
     encoder_one(S, in, S.h1 + threadIdx.x, out);
-    float* dst = acc + (size_t)sm.slot * DFB_LATENT_DIM;
+    long long* dst = acc + (size_t)sm.slot * DFB_LATENT_DIM;
 #pragma unroll
-    for (int l = 0; l < DFB_LATENT_DIM; ++l) atomicAdd(dst + l, out[l]);
+    for (int l = 0; l < DFB_LATENT_DIM; ++l) acc_add(dst + l, out[l]);
   }
 }
 
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(ENC_T, 1) encoder_explicit_kernel(const float*
 
 // map.py:450-453: one warp per touched slot
 __global__ void __launch_bounds__(256) ik_finalize_kernel(const int* __restrict__ counters, const int* __restrict__ touched,
-                                                          float* __restrict__ acc, int* __restrict__ acc_n, float* __restrict__ latents,
+                                                          long long* __restrict__ acc, int* __restrict__ acc_n, float* __restrict__ latents,
                                                           float* __restrict__ obs_count, uint8_t* __restrict__ updated, int* __restrict__ stats,
                                                           int n_new) {
   const int lane = threadIdx.x & 31;
@@ -322,10 +322,10 @@ __global__ void __launch_bounds__(256) ik_finalize_kernel(const int* __restrict_
     __syncwarp();
     if (lane < DFB_LATENT_DIM) {
       float* lp = latents + (size_t)slot * DFB_LATENT_DIM + lane;
-      float* ap = acc + (size_t)slot * DFB_LATENT_DIM + lane;
-      const float sum = __fadd_rn(*ap, __fmul_rn(*lp, cnt));   // :450
+      long long* ap = acc + (size_t)slot * DFB_LATENT_DIM + lane;
+      const float sum = __fadd_rn(acc_read(*ap), __fmul_rn(*lp, cnt));   // :450
       *lp = __fdiv_rn(sum, cnt_new);                           // :452
-      *ap = 0.f;
+      *ap = 0;
     }
     __syncwarp();
     if (lane == 0) { obs_count[slot] = cnt_new; acc_n[slot] = 0; updated[slot] = 1; }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) ik_finalize_kernel(const int* __restrict_
 
 namespace dfb {
 // tcgen05 encoder engine (encoder_tc.cu)
-int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, float* acc, cudaStream_t s);
+int tc_encoder_scatter(const void* samples, const int* m_dev, int m_max, const void* tc_blob, long long* acc, cudaStream_t s);
 int tc_encoder_explicit(const float* x6, int m, const void* tc_blob, float* out, cudaStream_t s);
 }  // namespace dfb
 
@@ -398,7 +398,7 @@ int dfb_integrate_plan(const dfb_map_params* h_params, const float* xyz, const f
 
 int dfb_integrate_commit(const dfb_map_params* h_params, const float* normal, const uint8_t* unq_mask, int n, int64_t* indexer,
                          float* latent_vecs, int64_t* latent_vecs_pos, float* voxel_obs_count, uint8_t* updated_flag,
-                         int64_t n_occupied, int64_t capacity, int32_t n_new, uint32_t* grid_bits, float* acc, int32_t* acc_n,
+                         int64_t n_occupied, int64_t capacity, int32_t n_new, uint32_t* grid_bits, int64_t* acc, int32_t* acc_n,
                          int32_t* touched, const float* encoder_blob, int32_t* d_stats, void* ws, size_t ws_bytes, void* stream) {
   DFB_CHECK_ARG(h_params && n >= 0 && d_stats, "integrate_commit");
   cudaStream_t s = (cudaStream_t)stream;
@@ -420,15 +420,15 @@ int dfb_integrate_commit(const dfb_map_params* h_params, const float* normal, co
                                                   w.counters, w.samples);
   DFB_LAUNCH_CHECK();
   if (encoder_engine() == 1) {
-    int rc = tc_encoder_scatter(w.samples, w.counters, n * 8, encoder_blob + EB_TOTAL, acc, s);
+    int rc = tc_encoder_scatter(w.samples, w.counters, n * 8, encoder_blob + EB_TOTAL, reinterpret_cast<long long*>(acc), s);
     if (rc) return rc;
   } else {
     DFB_CUDA(cudaFuncSetAttribute(encoder_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
     // the sample count lives on the device: persistent grid sized for the worst case (8 n samples), capped at the SM count
     const int enc_grid = std::min(sm_count(), div_up((long long)n * 8, ENC_T));
-    encoder_scatter_kernel<<<enc_grid, ENC_T, sizeof(EncSmem), s>>>(w.samples, w.counters, encoder_blob, acc);
+    encoder_scatter_kernel<<<enc_grid, ENC_T, sizeof(EncSmem), s>>>(w.samples, w.counters, encoder_blob, reinterpret_cast<long long*>(acc));
   }
-  ik_finalize_kernel<<<std::min(2 * sm_count(), div_up((long long)n * 32, 256)), 256, 0, s>>>(w.counters, touched, acc, acc_n, latent_vecs,
+  ik_finalize_kernel<<<std::min(2 * sm_count(), div_up((long long)n * 32, 256)), 256, 0, s>>>(w.counters, touched, reinterpret_cast<long long*>(acc), acc_n, latent_vecs,
                                                                                         voxel_obs_count, updated_flag, d_stats, n_new);
   DFB_LAUNCH_CHECK();
   return DFB_OK;

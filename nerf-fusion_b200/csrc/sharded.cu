@@ -24,7 +24,7 @@
 #include "common.cuh"
 
 namespace dfb {
-int tc_encoder_scatter_segments(const void* samples, const int* seg_counts, int n_seg, int seg_cap, const void* tc_blob, float* acc,
+int tc_encoder_scatter_segments(const void* samples, const int* seg_counts, int n_seg, int seg_cap, const void* tc_blob, long long* acc,
                                 cudaStream_t s);
 size_t encoder_tc_blob_offset_floats();
 
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) resolve_slots_kernel(Geo g, Sample* __res
 
 // map.py:450-453: one warp per touched slot; a voxel whose count reaches encoder_count_th leaves the candidate set: that
 // delta opens the next keyframe's list
-__global__ void __launch_bounds__(256) finalize_kernel(Geo g, int* __restrict__ counters, const int* __restrict__ touched, float* __restrict__ acc,
+__global__ void __launch_bounds__(256) finalize_kernel(Geo g, int* __restrict__ counters, const int* __restrict__ touched, long long* __restrict__ acc,
                                                        int* __restrict__ acc_n, float* __restrict__ latents, float* __restrict__ obs_count,
                                                        const int* __restrict__ pos, int* __restrict__ next_delta, int* __restrict__ n_next_delta,
                                                        int delta_cap) {
@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(Geo g, int* __restrict__ 
     __syncwarp();
     if (lane < DFB_LATENT_DIM) {
       float* lp = latents + (size_t)slot * DFB_LATENT_DIM + lane;
-      float* ap = acc + (size_t)slot * DFB_LATENT_DIM + lane;
-      *lp = __fdiv_rn(__fadd_rn(*ap, __fmul_rn(*lp, cnt)), cnt_new);
-      *ap = 0.f;
+      long long* ap = acc + (size_t)slot * DFB_LATENT_DIM + lane;
+      *lp = __fdiv_rn(__fadd_rn(acc_read(*ap), __fmul_rn(*lp, cnt)), cnt_new);
+      *ap = 0;
     }
     __syncwarp();
     if (lane == 0) {
@@ -474,9 +474,9 @@ int dfb_shard_phase5(const dfb_shard* S, const float* encoder_blob, int32_t* d_s
   resolve_slots_kernel<<<seg_grid(S->smp_cap, S->world), 256, 0, s>>>(g, reinterpret_cast<Sample*>(S->smp_inbox), S->smp_count, S->smp_cap,
                                                                      S->indexer_local, S->acc_n, S->touched, S->counters);
   DFB_LAUNCH_CHECK();
-  int rc = tc_encoder_scatter_segments(S->smp_inbox, S->smp_count, S->world, S->smp_cap, encoder_blob + encoder_tc_blob_offset_floats(), S->acc, s);
+  int rc = tc_encoder_scatter_segments(S->smp_inbox, S->smp_count, S->world, S->smp_cap, encoder_blob + encoder_tc_blob_offset_floats(), reinterpret_cast<long long*>(S->acc), s);
   if (rc) return rc;
-  finalize_kernel<<<2 * sm_count(), 256, 0, s>>>(g, S->counters, S->touched, S->acc, S->acc_n, S->latent_vecs, S->voxel_obs_count, S->latent_vecs_pos,
+  finalize_kernel<<<2 * sm_count(), 256, 0, s>>>(g, S->counters, S->touched, reinterpret_cast<long long*>(S->acc), S->acc_n, S->latent_vecs, S->voxel_obs_count, S->latent_vecs_pos,
                                                S->next_delta, S->n_next_delta, S->delta_cap);
   rearm_kernel<<<1, 256, 0, s>>>(S->counters, S->delta_list, S->next_delta, S->n_next_delta, S->delta_cap, d_stats);
   DFB_LAUNCH_CHECK();

@@ -188,7 +188,7 @@ class DenseIndexedMap:
         self._backing = new
         self._rows = rows
         # per-slot scratch of the integrate kernels (zero-invariant between calls) and the meshing dirty flags
-        self._acc = torch.zeros((rows, self.latent_dim), dtype=torch.float32, device=self.device)
+        self._acc = torch.zeros((rows, self.latent_dim), dtype=torch.int64, device=self.device)      # fixed-point sums (2^-34 units)
         self._acc_n = torch.zeros((rows,), dtype=torch.int32, device=self.device)
         self._touched = torch.zeros((rows,), dtype=torch.int32, device=self.device)
         self._updated_flag = flag

@@ -55,7 +55,7 @@ class _RankMemory:
         self.voxel_obs_count = z(self.capacity, dtype=torch.float32)
         self.cand_bits = z((G + 31) // 32 + 1)
         self.grid_count = z(self.n_local)
-        self.acc = z(self.capacity, L, dtype=torch.float32)
+        self.acc = z(self.capacity, L, dtype=torch.int64)           # fixed-point encoder sums (2^-34 units): order-independent
         self.acc_n = z(self.capacity)
         self.touched = z(self.capacity)
         self.counters = z(int(lib.dfb_shard_counter_ints()))

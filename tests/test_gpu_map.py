@@ -282,3 +282,22 @@ def test_integrate_random_scenes_vs_oracle(weights, seed, voxel, bmin, bmax, pru
         ref = om.latent_vecs[:nocc].numpy()
         assert np.abs(m.latent_vecs[:nocc].cpu().numpy() - ref).max() <= 1e-3 * max(np.abs(ref).max(), 1e-6)
     assert (om.voxel_obs_count[:nocc] >= 120.0).any()           # the candidate threshold was exercised
+
+
+def test_map_is_reproducible_bit_for_bit(weights, engine):
+    """The per-voxel encoder sums are 64-bit fixed-point (common.cuh acc_add): the same keyframes give the same latents bit for
+    bit however the scatter's atomics interleave -- unlike the float atomics of the reference (indexing.cu:59-71), whose maps
+    differ run to run (0.15 % of the voxel counts, latents up to 2.5 % on those voxels: profiles/r02_config1_parity*.json)."""
+    G = dict(np.load(GOLD / "map_golden.npz"))
+    Pw, Nw = torch.from_numpy(G["Pw"]).to(DEV), torch.from_numpy(G["Nw"]).to(DEV)
+    maps = []
+    for rep in range(3):
+        m = make_map(weights)
+        for shift in (torch.zeros(3), torch.from_numpy(G["k2_shift"])):
+            # a different point ORDER every repetition: the atomics land in a different order, the sums must not move
+            perm = torch.randperm(Pw.shape[0], generator=torch.Generator().manual_seed(rep)).to(DEV) if rep else torch.arange(Pw.shape[0], device=DEV)
+            m.integrate_keyframe((Pw + shift.to(DEV))[perm].contiguous(), Nw[perm].contiguous())
+        n = m.n_occupied
+        maps.append((m.latent_vecs_pos[:n].clone(), m.voxel_obs_count[:n].clone(), m.latent_vecs[:n].clone()))
+    for b in maps[1:]:
+        assert torch.equal(maps[0][0], b[0]) and torch.equal(maps[0][1], b[1]) and torch.equal(maps[0][2], b[2])

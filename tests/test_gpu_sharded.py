@@ -1,7 +1,7 @@
 """-m gpu: the sharded map's kernels and protocol (csrc/sharded.cu, nerf-fusion_b200/sharded.py) with ALL ranks of a world
 emulated in one process on one GPU (`LocalFabric`: peer pointers are plain pointers, phases run rank after rank -- no
 kernel waits for another, so this is exactly what each rank executes between two barriers).  Parity with the single-GPU
-DenseIndexedMap on {linear voxel id -> (count, latent)}: ids and counts bit-exact, latents 1e-3 relative (measured ~1e-6).
+DenseIndexedMap on {linear voxel id -> (count, latent)}: ids, counts AND latents bit-exact (fixed-point encoder sums).
 The multi-process path (CUDA IPC peer mappings + NCCL barrier) is exercised by tools/sharded_bench.py on 2..8 GPUs."""
 import numpy as np
 import pytest
@@ -25,10 +25,12 @@ def _check(fab, one, tag):
     assert torch.equal(ids, rid), f"{tag}: voxel ids differ ({ids.numel()} vs {rid.numel()})"
     assert torch.equal(cnt, rcnt), f"{tag}: counts differ"
     err = float((lat - rlat).abs().max() / rlat.abs().max())
-    assert err < 1e-3, (tag, err)
+    # the encoder sums are 64-bit fixed-point (integer adds commute) and a sample's encoding does not depend on the rank or tile
+    # that computes it: the sharded map is BIT-IDENTICAL to the single-GPU map, for any split of the points
+    assert torch.equal(lat, rlat), (tag, err)
     for m in fab.maps:                                               # zero invariants restored, no overflow
         st = m.read_stats()
-        assert int(m.mem.grid_count.abs().sum()) == 0 and int(m.mem.acc_n.sum()) == 0 and float(m.mem.acc.abs().sum()) == 0.0
+        assert int(m.mem.grid_count.abs().sum()) == 0 and int(m.mem.acc_n.sum()) == 0 and int(m.mem.acc.abs().sum()) == 0
     return err
 
 

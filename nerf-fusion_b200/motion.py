@@ -30,16 +30,23 @@ class Quaternion:
         else:
             self.q = np.array([1.0, 0.0, 0.0, 0.0])
 
+    # The 3x3 / 4-vector algebra below runs on Python floats (IEEE doubles, like numpy's float64) instead of small numpy
+    # arrays: a frame needs ~10 pose operations, and as numpy calls they cost 200 us of host time -- on the critical path
+    # between one frame's pose solve and the next (tools/pipeline_timeline.py); as float arithmetic ~25 us.
     def _unit(self):
-        n = np.linalg.norm(self.q)
-        return self.q / n if n > 0 else self.q
+        w, x, y, z = self.q.tolist()
+        n = math.sqrt(w * w + x * x + y * y + z * z)
+        return (w / n, x / n, y / n, z / n) if n > 0 else (w, x, y, z)
+
+    def _rot9(self):
+        w, x, y, z = self._unit()
+        return (1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y))
 
     @property
     def rotation_matrix(self):
-        w, x, y, z = self._unit()
-        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
-                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
-                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=np.float64)
+        return np.array(self._rot9(), dtype=np.float64).reshape(3, 3)
 
     @property
     def transformation_matrix(self):
@@ -47,30 +54,56 @@ class Quaternion:
         m[:3, :3] = self.rotation_matrix
         return m
 
+    @classmethod
+    def _raw(cls, q4):
+        o = cls.__new__(cls)
+        o.q = np.array(q4, dtype=np.float64)
+        return o
+
     @property
     def inverse(self):
-        w, x, y, z = self.q
-        return Quaternion(array=np.array([w, -x, -y, -z]) / float(np.dot(self.q, self.q)))
+        w, x, y, z = self.q.tolist()
+        n2 = w * w + x * x + y * y + z * z
+        return Quaternion._raw((w / n2, -x / n2, -y / n2, -z / n2))
 
     def __mul__(self, o):
-        a, b = self.q, o.q
-        return Quaternion(array=np.array([
-            a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
-            a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
-            a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
-            a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]]))
+        a0, a1, a2, a3 = self.q.tolist()
+        b0, b1, b2, b3 = o.q.tolist()
+        return Quaternion._raw((
+            a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3,
+            a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2,
+            a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1,
+            a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0))
+
+    def _rotate3(self, v):
+        r = self._rot9()
+        x, y, z = v
+        return (r[0] * x + r[1] * y + r[2] * z, r[3] * x + r[4] * y + r[5] * z, r[6] * x + r[7] * y + r[8] * z)
 
     def rotate(self, v):
-        return self.rotation_matrix @ np.asarray(v, dtype=np.float64)
+        v = np.asarray(v, dtype=np.float64)
+        if v.shape == (3,):
+            return np.array(self._rotate3(v.tolist()), dtype=np.float64)
+        return self.rotation_matrix @ v
 
     def __repr__(self):
         return f"Quaternion({self.q[0]!r}, {self.q[1]!r}, {self.q[2]!r}, {self.q[3]!r})"
 
 
 def _quat_from_matrix(M):
-    R = M[:3, :3]
-    if not np.allclose(R @ R.T, np.eye(3), rtol=1e-5, atol=1e-8) or not np.isclose(np.linalg.det(R), 1.0, rtol=1e-5, atol=1e-8):
-        raise ValueError("Matrix must be special orthogonal")      # same acceptance test as pyquaternion
+    R = M[:3, :3].tolist()
+    # the acceptance test of pyquaternion (allclose(R R^T, I) and isclose(det R, 1), rtol 1e-5, atol 1e-8), on floats
+    ok = True
+    for i in range(3):
+        for j in range(3):
+            v = R[i][0] * R[j][0] + R[i][1] * R[j][1] + R[i][2] * R[j][2]
+            e = 1.0 if i == j else 0.0
+            ok = ok and abs(v - e) <= 1e-8 + 1e-5 * e
+    det = (R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0])
+           + R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]))
+    if not ok or not abs(det - 1.0) <= 1e-8 + 1e-5:
+        raise ValueError("Matrix must be special orthogonal")
+    R = _Rows(R)
     tr = R[0, 0] + R[1, 1] + R[2, 2]
     if tr > 0:
         s = math.sqrt(tr + 1.0) * 2
@@ -85,6 +118,17 @@ def _quat_from_matrix(M):
         s = math.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
         q = [(R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s]
     return np.asarray(q, dtype=np.float64)
+
+
+class _Rows:
+    """R[i, j] on a list of lists (keeps the four-branch formula below readable)."""
+    __slots__ = ("r",)
+
+    def __init__(self, r):
+        self.r = r
+
+    def __getitem__(self, ij):
+        return self.r[ij[0]][ij[1]]
 
 
 def so3_wedge(p):
@@ -134,12 +178,22 @@ class Isometry:
             J = (s / angle) * np.identity(3) + (1 - s / angle) * np.outer(ax, ax) + ((1 - c) / angle) * so3_wedge(ax)
         return Isometry(q=Quaternion(matrix=R), t=J @ rho)
 
+    @classmethod
+    def _raw(cls, q, t3):
+        o = cls.__new__(cls)
+        o.q = q
+        o.t = np.array(t3, dtype=np.float64)
+        return o
+
     def inv(self):
         qi = self.q.inverse
-        return Isometry(q=qi, t=-(qi.rotate(self.t)))
+        x, y, z = qi._rotate3(self.t.tolist())
+        return Isometry._raw(qi, (-x, -y, -z))
 
     def dot(self, right):
-        return Isometry(q=self.q * right.q, t=self.q.rotate(right.t) + self.t)
+        x, y, z = self.q._rotate3(right.t.tolist())
+        a, b, c = self.t.tolist()
+        return Isometry._raw(self.q * right.q, (x + a, y + b, z + c))
 
     def torch_matrices(self, device):
         import torch

@@ -421,8 +421,8 @@ class SDFTracker:
                 levels[l].cur_I = Is[l].data_ptr(); levels[l].cur_D = Ds[l].data_ptr(); levels[l].cur_G = Gs[l].data_ptr()
                 levels[l].H, levels[l].W = int(Is[l].size(0)), int(Is[l].size(1))
         intr = (C.c_double * 4)(calib.fx, calib.fy, calib.cx, calib.cy) if calib is not None else None
-        lastp = (C.c_double * 12)(*last_pose.q.rotation_matrix.reshape(-1).tolist(), *last_pose.t.tolist())
-        deltap = (C.c_double * 12)(*delta_pose.q.rotation_matrix.reshape(-1).tolist(), *delta_pose.t.tolist())
+        lastp = (C.c_double * 12)(*last_pose.q._rot9(), *last_pose.t.tolist())
+        deltap = (C.c_double * 12)(*delta_pose.q._rot9(), *delta_pose.t.tolist())
         stats = (C.c_int32 * 8)()
         if self.time_kernels:
             stats[4] = 0x54494d45

@@ -192,6 +192,13 @@ static_assert(CW == 64, "one 64-bit ReLU mask per thread and layer");
 #endif
 __device__ __forceinline__ void mask_put(uint64_t& mk, int q, uint32_t m) { mk = (q == 0 ? 0ull : mk) | ((uint64_t)m << (16 * q)); }
 __device__ __forceinline__ uint32_t mask_get(uint64_t mk, int q) { return (uint32_t)(mk >> (16 * q)) & 0xffffu; }
+// Layers 0..2 keep their masks in PAIR layout (the forward epilogue works on packed half pairs): within a piece, element 2k is
+// bit k and element 2k+1 is bit 16 + k; the two pieces of a 32-bit word are 8 bits apart.  Layer 3 (heads, FP32) stays linear.
+__device__ __forceinline__ void mask_put_pairs(uint64_t& mk, int q, uint32_t m) {       // m: bits 0..7 | 16..23, already at the piece's offset
+  mk = (q == 0 ? 0ull : mk) | ((uint64_t)m << (32 * (q >> 1)));
+}
+__device__ __forceinline__ uint32_t mask_get_pairs(uint64_t mk, int q) { return (uint32_t)(mk >> (32 * (q >> 1))) >> (8 * (q & 1)); }
+#define DFB_PAIR_BIT(m, i) (((m) >> ((((i) & 1) << 4) + ((i) >> 1))) & 1u)
 __device__ __forceinline__ void store_a16(const Ctx& c, int k0, const float* h) {
   uint32_t hi[8], lo[8];
 #pragma unroll
@@ -219,17 +226,31 @@ __device__ __forceinline__ void epi_fwd(Ctx& c, int layer, int bias_off) {
     if (cb < NCOLS) {                       // warp-uniform
       float v[EW];
       tmem_ld16(tb + cb, v);
+      // ReLU, its mask and the hi / lo split on PACKED half pairs: x_hi = fp16(a), x_lo = fp16(a - x_hi) as before, then one
+      // half2 compare gives 0xffff per positive half, which zeroes hi and lo (two ANDs per pair instead of a compare, a max, a
+      // select and mask-bit logic per element) and, ANDed with a one-hot pair constant, IS the mask bit.  [a > 0] is taken on
+      // the rounded half: it differs from the FP32 test only for 0 < a < 2^-25, where hi and lo are zero anyway.
+      uint32_t hi[8], lo[8];
       uint32_t m = 0;
+      const uint32_t sel = 0x00010001u << (8 * (q & 1));
+      const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
       const float4* b4 = reinterpret_cast<const float4*>(sm + bias_off + cb);
 #pragma unroll
       for (int i4 = 0; i4 < EW / 4; ++i4) {
         const float4 b = b4[i4];
         const float a0 = v[4 * i4] + b.x, a1 = v[4 * i4 + 1] + b.y, a2 = v[4 * i4 + 2] + b.z, a3 = v[4 * i4 + 3] + b.w;
-        m |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * i4);
-        v[4 * i4] = fmaxf(a0, 0.f); v[4 * i4 + 1] = fmaxf(a1, 0.f); v[4 * i4 + 2] = fmaxf(a2, 0.f); v[4 * i4 + 3] = fmaxf(a3, 0.f);
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+        const uint32_t p01 = __hgt2_mask(h01, zero2), p23 = __hgt2_mask(h23, zero2);
+        hi[2 * i4] = *reinterpret_cast<const uint32_t*>(&h01) & p01; lo[2 * i4] = *reinterpret_cast<const uint32_t*>(&l01) & p01;
+        hi[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&h23) & p23; lo[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&l23) & p23;
+        m |= (p01 & (sel << (2 * i4))) | (p23 & (sel << (2 * i4 + 1)));
       }
-      mask_put(c.mask[layer], q, m);
-      store_a16(c, cb, v);
+      mask_put_pairs(c.mask[layer], q, m);
+      const uint32_t ta = lane_base(c) + (uint32_t)(cb >> 1);
+      tmem_st8(ta + TM_AH, hi);
+      tmem_st8(ta + TM_AL, lo);
     }
   }
 }
@@ -244,9 +265,9 @@ __device__ __forceinline__ void epi_bwd(Ctx& c, int layer) {
     if (cb < NCOLS) {
       float v[EW];
       tmem_ld16(tb + cb, v);
-      const uint32_t m = mask_get(c.mask[layer], q);
+      const uint32_t m = mask_get_pairs(c.mask[layer], q);
 #pragma unroll
-      for (int i = 0; i < EW; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+      for (int i = 0; i < EW; ++i) v[i] = DFB_PAIR_BIT(m, i) ? v[i] : 0.f;
       store_a16(c, cb, v);
     }
   }
@@ -375,14 +396,13 @@ __device__ __forceinline__ void backward(Ctx& c, float seed_z, float seed_u, flo
     const int cb = CW * c.part + EW * q;
     float v[EW];
     tmem_ld16(tb + cb, v);
-    const uint32_t m = mask_get(c.mask[0], q);
+    const uint32_t m = mask_get_pairs(c.mask[0], q);
     const float4* t4 = reinterpret_cast<const float4*>(sm + DS_W0X + 3 * cb);
 #pragma unroll
     for (int i4 = 0; i4 < EW / 4; ++i4) {
       const float4 ta = t4[3 * i4], tb_ = t4[3 * i4 + 1], tc_ = t4[3 * i4 + 2];     // taps of 4 consecutive units, 3 floats each
-      const uint32_t mm = m >> (4 * i4);
-      const float d0 = (mm & 1u) ? v[4 * i4] : 0.f, d1 = (mm & 2u) ? v[4 * i4 + 1] : 0.f;
-      const float d2 = (mm & 4u) ? v[4 * i4 + 2] : 0.f, d3 = (mm & 8u) ? v[4 * i4 + 3] : 0.f;
+      const float d0 = DFB_PAIR_BIT(m, 4 * i4) ? v[4 * i4] : 0.f, d1 = DFB_PAIR_BIT(m, 4 * i4 + 1) ? v[4 * i4 + 1] : 0.f;
+      const float d2 = DFB_PAIR_BIT(m, 4 * i4 + 2) ? v[4 * i4 + 2] : 0.f, d3 = DFB_PAIR_BIT(m, 4 * i4 + 3) ? v[4 * i4 + 3] : 0.f;
       ga[0] = fmaf(ta.x, d0, ga[0]); ga[1] = fmaf(ta.y, d0, ga[1]); ga[2] = fmaf(ta.z, d0, ga[2]);
       gb[0] = fmaf(ta.w, d1, gb[0]); gb[1] = fmaf(tb_.x, d1, gb[1]); gb[2] = fmaf(tb_.y, d1, gb[2]);
       ga[0] = fmaf(tb_.z, d2, ga[0]); ga[1] = fmaf(tb_.w, d2, ga[1]); ga[2] = fmaf(tc_.x, d2, ga[2]);

@@ -228,7 +228,8 @@ __device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, f
 __global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restrict__ sorted, int n,
                                                            const GridParams* gpp, const int* __restrict__ cell_start,
                                                            int nb_points, float radius, uint8_t* __restrict__ mask,
-                                                           const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
+                                                           const int* __restrict__ n_dev, int* __restrict__ flag = nullptr,
+                                                           uint8_t* __restrict__ dead = nullptr) {
   if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(128) radius_count_kernel(const float4* __restr
   }
   mask[__float_as_int(q.w)] = count >= nb_points ? 1 : 0;
   if (flag) flag[__float_as_int(q.w)] = count >= nb_points ? 1 : 0;     // fused path: the compaction's scan input, no separate pass
+  if (dead) dead[j] = count >= nb_points ? 0 : 1;                       // by position in `sorted`: lets the normals search reuse THIS grid
 }
 
 // pcproc.cu:21-96, same expression shapes (including the double-precision promotions through M_PI).
@@ -356,12 +358,17 @@ __device__ __forceinline__ float cell_gap(int d, float frac) {
 template <int K>
 __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
                                                          const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
-                                                         float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
+                                                         float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr,
+                                                         const uint8_t* __restrict__ dead = nullptr) {
   if (n_dev) n = *n_dev;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   GridParams g = *gpp;
   float4 q = sorted[j];
+  if (dead && dead[j]) {                          // a point the radius filter removed: no query, and never a candidate (below)
+    if (flag) flag[__float_as_int(q.w)] = 0;
+    return;
+  }
   int3 c = cell_coord(g, q.x, q.y, q.z);
   unsigned long long key[K];
 #pragma unroll
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(128, 4) normals_kernel(const float4* __restric
           }
           const int b = cell_start[row + za], e = cell_start[row + zb + 1];
           for (int k = b; k < e; ++k) {
+            if (dead && dead[k]) continue;
             const float4 p = sorted[k];
             const float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
             // entries beyond the radius can never be used (pcproc.cu:120 breaks at the first miss), except that the
@@ -477,14 +485,19 @@ __device__ __forceinline__ void nb_merge(unsigned long long (&top)[16], const un
 
 __global__ void __launch_bounds__(NB_T, 4) normals_batched_kernel(const float4* __restrict__ sorted, const float4* __restrict__ pc4, int n,
                                                                   const GridParams* gpp, const int* __restrict__ cell_start, int max_nn, float radius,
-                                                                  float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr) {
+                                                                  float3 cam, float* __restrict__ normals, const int* __restrict__ n_dev, int* __restrict__ flag = nullptr,
+                                                                  const uint8_t* __restrict__ dead = nullptr) {
   __shared__ unsigned long long s_batch[NB_CAP * NB_T];
   if (n_dev) n = *n_dev;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if ((j & ~31) >= n) return;                                        // whole warp past the end (warp-uniform)
-  const bool live = j < n;
+  bool live = j < n;
   const GridParams g = *gpp;
   const float4 q = sorted[live ? j : n - 1];
+  if (live && dead && dead[j]) {                                     // removed by the radius filter: no query, never a candidate
+    if (flag) flag[__float_as_int(q.w)] = 0;
+    live = false;
+  }
   const int3 c = cell_coord(g, q.x, q.y, q.z);
   unsigned long long top[16];
 #pragma unroll
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(NB_T, 4) normals_batched_kernel(const float4* 
           const int len = e - b;
           const int L = __reduce_max_sync(0xffffffffu, len);
           for (int k = 0; k < L; ++k) {
-            if (k < len) {
+            if (k < len && !(dead && dead[b + k])) {
               const float4 p = sorted[b + k];
               const float d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
               const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
@@ -941,7 +954,7 @@ size_t dfb_preprocess_ws_bytes(int H, int W) {
   Arena a(nullptr, 0);
   a.take<float>((size_t)n * 4); a.take<int>(n + 1); a.take<int>(n + 1); a.take<int>(n / 2048 + 8); a.take<int>(8);
   a.take<float>((size_t)n * 4); a.take<float>((size_t)n * 4); a.take<uint8_t>(n + 16); a.take<float>((size_t)n * 3);
-  a.take<float>((size_t)n * 3); a.take<float>((size_t)n * 3);
+  a.take<float>((size_t)n * 3); a.take<float>((size_t)n * 3); a.take<unsigned>(8); a.take<uint8_t>(n + 32);
   return a.off + dfb_pcproc_ws_bytes(n) + dfb_box_filter_ws_bytes(n) + 1024;
 }
 
@@ -977,28 +990,40 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   // P2: radius outlier filter (the kernel writes the compaction flags itself; rows past the device-side count are not scanned)
   rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0], nullptr, 0.f, true);
   if (rc) return rc;
-  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0], flag);
-  DFB_LAUNCH_CHECK();
-  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[1], s, &counts[0]);
-  if (rc) return rc;
-  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC, w.bbox);
-  // P3: normals
-  // (cell size from the density the radius filter's grid just measured: grid_params_kernel)
-  rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1], &counts[0], normal_radius * 0.5f, true);
-  if (rc) return rc;
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
-  if (max_nn <= 16 && !normals_use_v1())
-    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
-  else if (max_nn <= 16)
-    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
-  else
-    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcC), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, &counts[1], flag);
-  DFB_LAUNCH_CHECK();
-  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s, &counts[1]);
-  if (rc) return rc;
   unsigned* box_bbox = a.take<unsigned>(8);
+  uint8_t* dead = a.take<uint8_t>(n + 32);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcC, nrmC, flag, pos, n, &counts[1], pD, nD, box_bbox);
+  // One grid serves both searches when its cells (edge = the outlier radius) are no larger than half the normal radius (the
+  // reference's 0.05 / 0.1 m): the radius filter marks the points it removes BY POSITION in the sorted array, the kNN search
+  // skips them as queries and as candidates, and works on the uncompacted cloud B -- no second grid build (7 launches) and no
+  // compaction between the two stages (3 launches).  Indices are B's, whose order is C's: same neighbours, same tie-breaks.
+  const bool one_grid = outlier_radius * 2.0f <= normal_radius * 1.0001f && getenv("DFB_TWO_GRIDS") == nullptr;
+  const float* pcN = pcB;                                   // the cloud the normals index
+  const int* nN = &counts[0];
+  radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0], flag,
+                                                     one_grid ? dead : nullptr);
+  DFB_LAUNCH_CHECK();
+  if (!one_grid) {
+    rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[1], s, &counts[0]);
+    if (rc) return rc;
+    compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcB, flag, pos, n, &counts[0], pcC, w.bbox);
+    // P3: normals (cell size from the density the radius filter's grid just measured: grid_params_kernel)
+    rc = build_grid(pcC, n, normal_radius / NORMAL_SUB, GRID_CAP, w, s, &counts[1], &counts[0], normal_radius * 0.5f, true);
+    if (rc) return rc;
+    pcN = pcC; nN = &counts[1];
+  }
+  const uint8_t* dd = one_grid ? dead : nullptr;
+  if (max_nn <= 16 && !normals_use_v1())
+    normals_batched_kernel<<<div_up(n, NB_T), NB_T, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcN), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, nN, flag, dd);
+  else if (max_nn <= 16)
+    normals_kernel<16><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcN), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, nN, flag, dd);
+  else
+    normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcN), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, nN, flag, dd);
+  DFB_LAUNCH_CHECK();
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s, nN);
+  if (rc) return rc;
+  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcN, nrmC, flag, pos, n, nN, pD, nD, box_bbox);
   DFB_LAUNCH_CHECK();
   // P4: box filter
   return box_filter_impl(pD, nD, n, &counts[2], box_voxel, div_mode, out_points, out_normals, d_n_out, a, s, box_bbox);

@@ -126,7 +126,7 @@ SIGNATURES = {
 # counted against the ncu launch list of the bench, profiles/r02_launches_final.txt, minus the second grid build)
 KERNELS_PER_CALL = {
     "dfb_ingest_frame": 1, "dfb_transform_points": 1, "dfb_unproject_depth": 1, "dfb_remove_radius_outlier": 9, "dfb_estimate_normals": 9, "dfb_scatter_mean": 5,
-    "dfb_point_box_filter": 13, "dfb_preprocess_frame": 28, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_frame_images": 2, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
+    "dfb_point_box_filter": 13, "dfb_preprocess_frame": 25, "dfb_groupby_sum": 1, "dfb_gradient_xy": 1, "dfb_frame_images": 2, "dfb_rgb_odometry": 1, "dfb_rgb_hg": 2,
     "dfb_integrate_plan": 5, "dfb_integrate_commit": 4, "dfb_encoder_forward": 1, "dfb_decoder_forward": 1,
     "dfb_get_sdf": 1, "dfb_sdf_hg": 2, "dfb_gauss_newton": 0, "dfb_decode_cubes": 3, "dfb_marching_cubes": 1,
     "gn_kernel": 1,                    # launched inside dfb_gauss_newton (count reported through h_stats[7])

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float* __restrict
   if (i >= n) return;
   GridParams g = *gpp;
   float4 p = reinterpret_cast<const float4*>(pc4)[i];
+  if (isnan(p.x)) { cell_of[i] = -1; return; }      // an invalid row of an uncompacted cloud (fused preprocessing): in no cell
   int3 c = cell_coord(g, p.x, p.y, p.z);
   int id = (c.x * g.ny + c.y) * g.nz + c.z;
   cell_of[i] = id;
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restri
   if (i >= n) return;
   float4 p = reinterpret_cast<const float4*>(pc4)[i];
   int c = cell_of[i];
+  if (c < 0) return;
   // `cursor` IS the cell-count array: counting it back down to zero hands out the slots of the cell (in reverse) and leaves the
   // array cleared for the next grid -- no zeroing pass between the count and the scatter
   int pos = cell_start[c] + atomicSub(&cursor[c], 1) - 1;
@@ -565,7 +567,7 @@ __device__ __forceinline__ void bbox_init_inline(unsigned* bbox) {   // bbox_ini
   else if (t == 6) { bbox[7] = bbox[6]; bbox[6] = 0u; }
 }
 static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, cudaStream_t s, const int* n_dev = nullptr,
-                      const int* hint_n = nullptr, float cell_max = 0.f, bool bbox_ready = false) {
+                      const int* hint_n = nullptr, float cell_max = 0.f, bool bbox_ready = false, int* total_out = nullptr) {
   if (!bbox_ready) bbox_init_kernel<<<1, 32, 0, s>>>(w.bbox);     // (the fused path has the preceding compaction kernel do it)
   bbox_kernel<<<min(div_up(n, 256), 2 * sm_count()), 256, 0, s>>>(pc4, n, 4, w.bbox, n_dev);
   grid_params_kernel<<<1, 1, 0, s>>>(w.bbox, cell, cap, w.gp, hint_n, cell_max);
@@ -573,7 +575,7 @@ static int build_grid(const float* pc4, int n, float cell, int cap, GridWs& w, c
   zero_words_dev(w.cell_count, cap + 1, &w.gp->ncell1, s);
   grid_count_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.gp, w.cell_of, w.cell_count, n_dev, w.bbox);
   DFB_LAUNCH_CHECK();
-  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, nullptr, s, &w.gp->ncell1);
+  int rc = exclusive_scan_i32(w.cell_count, w.cell_start, cap + 1, w.block_sums, total_out, s, &w.gp->ncell1);   // total = rows in cells
   if (rc) return rc;
   grid_scatter_kernel<<<div_up(n, 256), 256, 0, s>>>(pc4, n, w.cell_of, w.cell_start, w.cell_count, w.sorted, n_dev);
   DFB_LAUNCH_CHECK();
@@ -742,13 +744,16 @@ __global__ void __launch_bounds__(256) groupby_sum_kernel(const float* __restric
 
 // ---- fused preprocessing helpers -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) unproject_sub_kernel(const float* __restrict__ depth, int H, int W, int Hs, int Ws, float fx, float fy,
-                                                            float cx, float cy, float* __restrict__ pc4, int* __restrict__ flag) {
+                                                            float cx, float cy, float* __restrict__ pc4, int* __restrict__ flag,
+                                                            int nan_invalid = 0, unsigned* init_bbox = nullptr) {
+  if (init_bbox && blockIdx.x == 0) bbox_init_inline(init_bbox);     // for the grid build that follows (no compaction in between)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Hs * Ws) return;
   const int v = i / Ws, u = i - v * Ws;
   const float d = depth[(size_t)(2 * v) * W + 2 * u];       // F.interpolate(scale 0.5, nearest) == depth[2v][2u]
   const bool ok = !isnan(d);
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  // nan_invalid: the cloud stays uncompacted; its invalid rows are NaN so that the bounding box and the grid skip them
+  float4 p = nan_invalid ? make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
   if (ok) { p.x = ((float)u - cx) / fx * d; p.y = ((float)v - cy) / fy * d; p.z = d; }
   reinterpret_cast<float4*>(pc4)[i] = p;
   flag[i] = ok ? 1 : 0;
@@ -972,7 +977,8 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   int* pos = a.take<int>(n + 17);
   int* bsums = a.take<int>((n + 16) / 2048 + 8);
   int* counts = a.take<int>(8);                             // [0] nA, [1] nB, [2] nC
-  float* pcB = a.take<float>((size_t)(n + 16) * 4);
+  float* pcB_buf = a.take<float>((size_t)(n + 16) * 4);
+  const float* pcB = pcB_buf;
   float* pcC = a.take<float>((size_t)(n + 16) * 4);
   uint8_t* mask = a.take<uint8_t>(n + 32);
   float* nrmC = a.take<float>((size_t)(n + 16) * 3);
@@ -981,24 +987,35 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   GridWs w;
   grid_ws_layout(a, n + 16, &w);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
+  // One grid serves both searches when its cells (edge = the outlier radius) are no larger than half the normal radius (the
+  // reference's 0.05 / 0.1 m): the cloud stays UNCOMPACTED from the unprojection to the box filter (invalid rows are NaN and in
+  // no cell), the radius filter marks the points it removes by position in the sorted array, the kNN search skips them as
+  // queries and as candidates -- no second grid build (7 launches) and no compaction before either stage (2 x 3 launches).
+  // Row indices are pixel indices, whose order is the order of the compacted clouds: same neighbours, same tie-breaks.
+  const bool one_grid = outlier_radius * 2.0f <= normal_radius * 1.0001f && getenv("DFB_TWO_GRIDS") == nullptr;
+  int rc;
   // P1: nearest x0.5 subsample (tracker.py:91-93) + unproject with halved intrinsics (:97-98) + validity flags
-  unproject_sub_kernel<<<div_up(n, 256), 256, 0, s>>>(depth, H, W, Hs, Ws, fx * 0.5f, fy * 0.5f, cx * 0.5f, cy * 0.5f, pcA, flag);
-  DFB_LAUNCH_CHECK();
-  int rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[0], s);
-  if (rc) return rc;
-  compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB, w.bbox);
-  // P2: radius outlier filter (the kernel writes the compaction flags itself; rows past the device-side count are not scanned)
-  rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0], nullptr, 0.f, true);
-  if (rc) return rc;
+  if (one_grid) {
+    unproject_sub_kernel<<<div_up(n, 256), 256, 0, s>>>(depth, H, W, Hs, Ws, fx * 0.5f, fy * 0.5f, cx * 0.5f, cy * 0.5f, pcA, flag, 1, w.bbox);
+    DFB_LAUNCH_CHECK();
+    pcB = pcA;
+    // P2: radius outlier filter; counts[0] = rows that are in a cell = valid rows (the scan's total)
+    rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, nullptr, nullptr, 0.f, true, &counts[0]);
+    if (rc) return rc;
+  } else {
+    unproject_sub_kernel<<<div_up(n, 256), 256, 0, s>>>(depth, H, W, Hs, Ws, fx * 0.5f, fy * 0.5f, cx * 0.5f, cy * 0.5f, pcA, flag);
+    DFB_LAUNCH_CHECK();
+    rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[0], s);
+    if (rc) return rc;
+    compact4_kernel<<<div_up(n, 256), 256, 0, s>>>(pcA, flag, pos, n, nullptr, pcB_buf, w.bbox);
+    // P2: radius outlier filter (the kernel writes the compaction flags itself; rows past the device-side count are not scanned)
+    rc = build_grid(pcB, n, outlier_radius, GRID_CAP_COARSE, w, s, &counts[0], nullptr, 0.f, true);
+    if (rc) return rc;
+  }
   const float3 cam = make_float3(h_cam_xyz[0], h_cam_xyz[1], h_cam_xyz[2]);
   unsigned* box_bbox = a.take<unsigned>(8);
   uint8_t* dead = a.take<uint8_t>(n + 32);
   if (!a.ok()) { set_error("workspace too small: need %zu", a.off); return DFB_E_WORKSPACE; }
-  // One grid serves both searches when its cells (edge = the outlier radius) are no larger than half the normal radius (the
-  // reference's 0.05 / 0.1 m): the radius filter marks the points it removes BY POSITION in the sorted array, the kNN search
-  // skips them as queries and as candidates, and works on the uncompacted cloud B -- no second grid build (7 launches) and no
-  // compaction between the two stages (3 launches).  Indices are B's, whose order is C's: same neighbours, same tie-breaks.
-  const bool one_grid = outlier_radius * 2.0f <= normal_radius * 1.0001f && getenv("DFB_TWO_GRIDS") == nullptr;
   const float* pcN = pcB;                                   // the cloud the normals index
   const int* nN = &counts[0];
   radius_count_kernel<<<div_up(n, 128), 128, 0, s>>>(w.sorted, n, w.gp, w.cell_start, nb_points, outlier_radius, mask, &counts[0], flag,
@@ -1021,9 +1038,10 @@ int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, f
   else
     normals_kernel<32><<<div_up(n, 128), 128, 0, s>>>(w.sorted, reinterpret_cast<const float4*>(pcN), n, w.gp, w.cell_start, max_nn, normal_radius, cam, nrmC, nN, flag, dd);
   DFB_LAUNCH_CHECK();
-  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s, nN);
+  // (one grid: rows are pixel indices, all n of them carry a flag -- invalid pixels 0 from the unprojection)
+  rc = exclusive_scan_i32(flag, pos, n, bsums, &counts[2], s, one_grid ? nullptr : nN);
   if (rc) return rc;
-  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcN, nrmC, flag, pos, n, nN, pD, nD, box_bbox);
+  compact_pn_kernel<<<div_up(n, 256), 256, 0, s>>>(pcN, nrmC, flag, pos, n, one_grid ? nullptr : nN, pD, nD, box_bbox);
   DFB_LAUNCH_CHECK();
   // P4: box filter
   return box_filter_impl(pD, nD, n, &counts[2], box_voxel, div_mode, out_points, out_normals, d_n_out, a, s, box_bbox);

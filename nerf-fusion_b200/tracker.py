@@ -81,9 +81,8 @@ class SDFTracker:
         self._fe_choice = None             # (key, set) the last graphed front-end call replayed
         self._fe_cur = {}                  # key -> graph set the frame being tracked right now uses
         # Frame pipelining: track_camera(..., next_frame=(rgb, depth)) / prefetch_frame() enqueue the NEXT frame's front end on
-        # a side stream before this frame's pose solve is queued, so the ~60 small front-end kernels fill the SMs the solve
-        # leaves idle (its partial tile round, the serial step, the gaps between evaluations).  Three graph sets rotate:
-        # last committed frame (read as last_*), current frame, prefetched frame.
+        # a side stream (when: see prefetch_mode below), so that the GPU does not idle while the host does a frame's bookkeeping.
+        # Three graph sets rotate: last committed frame (read as last_*), current frame, prefetched frame.
         self._pf = None                    # pending prefetch: dict(rgb, depth, base, idx, ent, event)
         self._pf_stream = None
         # The pose solve is the critical path of a frame; with a prefetched front end running beside it, it is launched on a
@@ -278,8 +277,9 @@ class SDFTracker:
         """tracker.py:75-134.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid.
         depth_cut = (near, far), optional: depths outside the range become NaN here (what main.py:56-57 does before the
         call), so the clipping is part of the captured front end instead of five eager launches.
-        next_frame = (rgb, depth), optional: the frame that will be tracked next; its front end is queued on the side stream
-        (prefetch_frame) before this frame's pose solve, and runs under it."""
+        next_frame = (rgb, depth), optional: the frame that will be tracked next (tensors that stay untouched until the call that
+        tracks them); its front end is queued on the side stream (prefetch_frame) the moment this frame's pose solve has returned
+        (prefetch_mode "after", default) or ahead of the solve ("before")."""
         if self.fused_preprocess and self.sdf_args.subsample == 0.5:
             graphed = self.graph_frontend
             fe = self._frontend_graphed if graphed else self._frontend

@@ -270,7 +270,7 @@ def preprocess_frame(depth, fx, fy, cx, cy, nb_points=16, outlier_radius=0.05, m
     n_max = (H // 2) * (W // 2)
     out_p = torch.empty((n_max, 3), dtype=torch.float32, device=dev)
     out_n = torch.empty((n_max, 3), dtype=torch.float32, device=dev)
-    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)      # always written (the box filter's scan total; -1 on overflow)
     lib = _lib.load()
     if ws is None:
         ws = _WS.get(dev, lib.dfb_preprocess_ws_bytes(H, W))

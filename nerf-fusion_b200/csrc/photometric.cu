@@ -1,5 +1,6 @@
 // Photometric term: Sobel gradients, per-pixel residual/Jacobian (drop-in ops) and the fused H/g reduction.
 // Reference: system/ext/imgproc/photometric.cu:3-138, system/tracker.py:136-177.
+#include <cstdlib>
 #include "common.cuh"
 #include "photometric.cuh"
 #include "gn_step.cuh"
@@ -240,6 +241,10 @@ __global__ void __launch_bounds__(HG_T) rgb_step_gn_kernel(const float* prev_I, 
                                                            int with_J, GnShared* gs, int gi, gn::StepArgs sa) {
   __shared__ __align__(16) unsigned char scratch[gn::STEP_SCRATCH_BYTES];
   __shared__ int flag;
+  // programmatic dependent launch (like gn_eval_kernel): the blocks are placed while the previous evaluation's last block still
+  // runs its step; everything this kernel reads from `gs` comes after the dependency wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (gs->done[gi]) {
     if (blockIdx.x == 0 && threadIdx.x < 32) gn::skip_record(gs, sa);
     return;
@@ -279,12 +284,24 @@ int launch_rgb_step_gn(const dfb_rgb_level* L, const float* intr4, float min_gra
   P.fx = intr4[0]; P.fy = intr4[1]; P.cx = intr4[2]; P.cy = intr4[3];
   P.min_grad_scale = min_grad_scale; P.max_depth_delta = max_depth_delta;
   const long long npx = (long long)L->H * L->W;
-  if (npx >= 4LL * HG_T * 148)
-    rgb_step_gn_kernel<4><<<div_up(npx, HG_T * 4), HG_T, 0, s>>>(L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust,
-                                                                robust_k, compute_J, gs, gi, *sa);
-  else
-    rgb_step_gn_kernel<1><<<div_up(npx, HG_T), HG_T, 0, s>>>(L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust,
-                                                            robust_k, compute_J, gs, gi, *sa);
+  static const bool no_pdl = getenv("DFB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(HG_T); cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t e;
+  if (npx >= 4LL * HG_T * 148) {
+    cfg.gridDim = dim3(div_up(npx, HG_T * 4));
+    e = cudaLaunchKernelEx(&cfg, rgb_step_gn_kernel<4>, L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust, robust_k,
+                           compute_J, gs, gi, *sa);
+  } else {
+    cfg.gridDim = dim3(div_up(npx, HG_T));
+    e = cudaLaunchKernelEx(&cfg, rgb_step_gn_kernel<1>, L->prev_I, L->prev_D, L->cur_I, L->cur_D, L->cur_G, L->H, L->W, P, robust, robust_k,
+                           compute_J, gs, gi, *sa);
+  }
+  if (e != cudaSuccess) { set_error("rgb_step_gn launch: %s", cudaGetErrorString(e)); return DFB_E_CUDA; }
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

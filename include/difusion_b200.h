@@ -112,9 +112,12 @@ int dfb_point_box_filter(const float* points, const float* normals, int n, float
 
 /* The geometry half of SDFTracker.track_camera (tracker.py:89-120) as ONE asynchronous call with no host
  * synchronisation: nearest x0.5 subsample of the (H,W) depth (NaN = invalid), unproject with halved intrinsics, drop
- * invalid pixels, radius-outlier filter, PCA normals, drop NaN normals, 2 cm box filter.  Compactions keep row order
- * (like the reference's boolean-mask indexing), intermediate counts stay on the device.  out_points/out_normals hold up
- * to (H/2)*(W/2) rows; *d_n_out (device int32) receives the number of rows (-1: box-filter key range overflow). */
+ * invalid pixels, radius-outlier filter, PCA normals, drop NaN normals, 2 cm box filter.  Rows keep their order (like the
+ * reference's boolean-mask indexing), intermediate counts stay on the device.  When outlier_radius <= normal_radius / 2
+ * (the reference's 0.05 / 0.1 m) the cloud stays uncompacted until the box filter and ONE uniform grid (cells = the outlier
+ * radius) serves both the radius count and the kNN search; otherwise each stage compacts and builds its own grid.  Same rows,
+ * bit for bit, as the op-by-op chain either way.  out_points/out_normals hold up to (H/2)*(W/2) rows; *d_n_out (device int32)
+ * receives the number of rows (-1: box-filter key range overflow). */
 size_t dfb_preprocess_ws_bytes(int H, int W);
 int dfb_preprocess_frame(const float* depth, int H, int W, float fx, float fy, float cx, float cy, int nb_points,
                          float outlier_radius, int max_nn, float normal_radius, const float* h_cam_xyz, float box_voxel,

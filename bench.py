@@ -196,7 +196,7 @@ def run_ours(args):
     # >= 4 warm-up frames: an eager frame, two frames during which the three front-end graph sets are captured, and one frame
     # that prefetches nothing, so that the first timed frame runs its own front end inside the timed region
     K, Wm = args.steps, max(args.warmup, 4)
-    pipeline = os.environ.get("BENCH_NO_PIPELINE") != "1"      # frame t+1's front end queued under frame t's pose solve
+    pipeline = os.environ.get("BENCH_NO_PIPELINE") != "1"      # frame t+1 announced to the tracker (SDFTracker.prefetch_frame)
     profile_region = os.environ.get("BENCH_PROFILE_REGION") == "1"
     n_frames = K + Wm
     calib = dfb.FrameIntrinsic(*dfb.synth.ICL_CALIB)
@@ -384,8 +384,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "frames_per_rank": K, "points_per_frame": res["n_points"], "voxels": res["n_occupied"],
                    "sdf_gn_evals_per_frame": round(res["sdf_evals"] / n_frames, 1), "rgb_gn_evals_per_frame": round(res["rgb_evals"] / n_frames, 1),
                    "l2": "flushed before every frame (192 MiB write)",
-                   "pipeline": ("frame t+1's front end queued on a side stream under frame t's pose solve (exactly K front ends and K solves "
-                                "inside the timed region)") if pipeline else "off", "parallelism": "replicas" if world > 1 else "single",
+                   "pipeline": ("frame t+1's front end queued on a side stream the moment frame t's pose solve has returned, i.e. while the host "
+                                "does frame t's bookkeeping (exactly K front ends and K solves inside the timed region)") if pipeline else "off", "parallelism": "replicas" if world > 1 else "single",
                    "max_track_err_m": round(res["track_err"], 5), "timed_by": "cuda events around the K-frame loop, max over ranks",
                    "wall_s": round(res["wall"], 3), "sharded": sharded},
         "clocks": res["clocks"],

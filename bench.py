@@ -173,7 +173,7 @@ def gen_frames(dfb, n, device, seed):
 def refresh(dfb, m, trk, frame_id, depth, rgb, calib, first_iso, integrate_interval=20, depth_cut=(0.5, 5.0), next_frame=None):
     """main.py:42-102 without the GUI: depth cut, track, integrate every `integrate_interval` frames.
     next_frame = (depth, rgb) of the frame that follows (a camera delivers frames ahead of their processing): its front end is
-    queued on the tracker's side stream before this frame's pose solve (SDFTracker.prefetch_frame)."""
+    queued on the tracker's side stream the moment this frame's pose solve has returned (SDFTracker.prefetch_frame)."""
     pose = trk.track_camera(rgb, depth, calib, first_iso if len(trk.all_pd_pose) == 0 else None, depth_cut=depth_cut,
                             next_frame=None if next_frame is None else (next_frame[1], next_frame[0]))
     pc, nrm = trk.last_processed_pc

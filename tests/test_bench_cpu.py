@@ -29,8 +29,13 @@ def test_committed_evidence_is_readable():
     assert t is not None and 1e5 < t < 1e9                      # DRAM bytes per launch of the dominant kernel, from profiles/
     pk = bench.peaks()
     assert pk["bf16_sustained"] > 100 and pk["hbm"] > 1000
-    final = json.loads((ROOT / "profiles" / "r01_bench_final.json").read_text().strip().splitlines()[-1])
-    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
-        assert key in final, key
-    assert final["gpu_launches"] > 0 and final["roofline"]["frac"] == round(final["roofline"]["achieved"] / final["roofline"]["peak"], 5)
+    for name in ("r01_bench_final.json", "r02_bench_final.json"):
+        final = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                    "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+            assert key in final, (name, key)
+        assert final["gpu_launches"] > 0 and final["roofline"]["frac"] == round(final["roofline"]["achieved"] / final["roofline"]["peak"], 5)
+    # round 2 adds the reference's own CUDA path timed on the same GPU and the parity of the DEFAULT engines against it
+    assert final["cuda_reference"]["value"] > 0 and final["parity"]["voxel_ids_equal"] is True
+    assert final["parity"]["H_rel_on_reference_map"] < 1e-4 and final["parity"]["sdf_max_abs_m_on_reference_map"] < 1e-4
+    assert final["e2e"]["h2d_bytes_per_step"] > 0 and final["clocks"]["reasons"] == []
